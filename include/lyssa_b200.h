@@ -1,0 +1,176 @@
+/* lyssa_b200.h — C-ABI of the B200-native Batch-OMP / K-SVD / ODL engine.
+ *
+ * Drop-in boundary for ONE hot path of ektormak/Lyssandra (paths relative to the reference
+ * tree): lyssa.sparse_coding.sparse_encoder(algorithm='bomp').encode() and the
+ * lyssa.dict_learning approximate-K-SVD / online learners that consume its codes.  The
+ * reference has no FFI of its own (pure Python over NumPy/OpenBLAS); each entry point below
+ * names the reference call site it replaces.  INTEGRATION.md shows the ctypes stub a
+ * maintainer would add at those call sites.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative LYS_E* code on failure;
+ *    lys_last_error() returns a thread-local message for the last failure.
+ *  - unless the name ends in _host, all data pointers are DEVICE pointers of the current
+ *    device; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *    Calls are asynchronous with respect to the host unless stated otherwise.
+ *  - the library never allocates caller-visible memory: ask *_workspace_bytes() and pass a
+ *    scratch buffer (256-byte aligned).
+ *  - arithmetic is float32, indices int32.  "signal" = one datapoint (a column of the
+ *    reference's X); "atom" = one dictionary column.
+ *  - strides are in ELEMENTS.  The reference keeps signals in columns, X(n,N) C-order:
+ *    x_feat_stride = N, x_sig_stride = 1.  Signal-major storage (N,n): x_feat_stride = 1,
+ *    x_sig_stride = n.  D is the reference's (n,K) C-order array: D[f*ldd + atom].
+ *  - sparse codes are (idx,val)[N][k]: the atoms of signal i in SELECTION order, unused
+ *    slots padded with idx = -1, val = 0 (a signal may stop early, see lys_bomp_encode).
+ */
+#ifndef LYSSA_B200_H
+#define LYSSA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define LYS_API __attribute__((visibility("default")))
+#else
+#define LYS_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LYS_OK            0
+#define LYS_EINVAL       -1   /* bad argument (shape, stride, null pointer, k out of range) */
+#define LYS_ECUDA        -2   /* a CUDA runtime call or kernel launch failed */
+#define LYS_EWORKSPACE   -3   /* workspace too small */
+#define LYS_EUNSUPPORTED -4   /* shape outside what the kernels are built for */
+
+#define LYS_MAX_NONZERO   32  /* k  <= 32 */
+#define LYS_MAX_ATOMS   4096  /* K  <= 4096 */
+#define LYS_MAX_FEATURES 256  /* n  <= 256 */
+
+/* ---- library ------------------------------------------------------------------------ */
+LYS_API int         lys_version(void);                 /* 10000*major + 100*minor + patch */
+LYS_API const char* lys_last_error(void);
+/* SM count / compute capability of `device`; fails unless it is an sm_100 part. */
+LYS_API int         lys_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- K1: Gram = D^T D --------------------------------------------------------------
+ * replaces `Gram = fast_dot(D.T, D)`, lyssa/sparse_coding.py:630.  G is (K,K) row-major. */
+LYS_API int lys_gram(const float* D, int64_t ldd, int n, int K, float* G, void* stream);
+
+/* ---- K2+K3+K4: Batch-OMP encode -------------------------------------------------------
+ * replaces `Alpha = fast_dot(D.T, X)` (sparse_coding.py:631) and
+ * run_parallel(batch_omp, ...) (sparse_coding.py:718 -> :302-367), including the dense
+ * zero-fill + scatter `Z[Dx, i] = z` (:308,:365; lyssa/utils/__init__.py:69,89).
+ *
+ * Semantics mirrored from batch_omp: first-maximum argmax of |alpha| (:322); stop when the
+ * picked atom is already selected (:323-325) or the Cholesky pivot 1 - w.w drops below
+ * machine epsilon of the compute type (:335,:345); the atom self-product is the literal 1
+ * (:334,:337,:344) so D must have unit-norm columns; `tol` does not exist (the reference
+ * ignores it, :302,:536).
+ *
+ * Outputs: idx,val (N,k) as described above; nsel (N) number of atoms selected (may be
+ * NULL); Z (optional, may be NULL) the dense code matrix the reference returns, written in
+ * full (zeros included): element (atom c, signal i) at Z[c*z_atom_stride + i*z_sig_stride].
+ * z_atom_stride = 1, z_sig_stride >= K (signal-major, returned to Python as a transposed
+ * view) is the fast layout. */
+LYS_API size_t lys_bomp_workspace_bytes(int n, int K, int64_t N, int k);
+LYS_API int lys_bomp_encode(const float* X, int64_t x_feat_stride, int64_t x_sig_stride,
+                    const float* D, int64_t ldd, const float* G,
+                    int n, int K, int64_t N, int k,
+                    int32_t* idx, float* val, int32_t* nsel,
+                    float* Z, int64_t z_atom_stride, int64_t z_sig_stride,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same call for HOST buffers (what `sparse_encoder.encode(X, D)` is for NumPy arrays):
+ * uploads D, forms the Gram matrix, streams X through the device in chunks with copies
+ * overlapped with compute, writes idx/val/nsel and/or dense Z back to host memory.
+ * Synchronous.  Pinned host buffers give full PCIe bandwidth; pageable ones work.
+ * Any of idx/val/nsel/Z may be NULL.  `device` < 0 means the current device. */
+LYS_API int lys_bomp_encode_host(const float* X, int64_t x_feat_stride, int64_t x_sig_stride,
+                         const float* D, int64_t ldd,
+                         int n, int K, int64_t N, int k,
+                         int32_t* idx, float* val, int32_t* nsel,
+                         float* Z, int64_t z_atom_stride, int64_t z_sig_stride,
+                         int device);
+
+/* Dense Z from sparse codes (zero-fill + scatter), same Z addressing as above.
+ * replaces `Z = np.zeros(...)` + `Z[Dx, i] = z`, sparse_coding.py:308,:365. */
+LYS_API int lys_codes_to_dense(const int32_t* idx, const float* val, int64_t N, int k, int K,
+                       float* Z, int64_t z_atom_stride, int64_t z_sig_stride, void* stream);
+
+/* ---- K5+K10: residual and approximation error from sparse codes ------------------------
+ * replaces `R = Y - fast_dot(D, X)` (lyssa/dict_learning/ksvd.py:103) and
+ * approx_error = ||X - D Z||_F^2 (lyssa/dict_learning/utils.py:14-19).
+ * R (optional) is signal-major (N,n), row stride n.  err (optional) is ONE device double.
+ * workspace: lys_residual_workspace_bytes. */
+LYS_API size_t lys_residual_workspace_bytes(int n, int K, int64_t N);
+LYS_API int lys_residual(const float* X, int64_t x_feat_stride, int64_t x_sig_stride,
+                 const float* D, int64_t ldd, const int32_t* idx, const float* val,
+                 int n, int K, int64_t N, int k, float* R, double* err,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K6: users-of-atom index (CSR by atom) ---------------------------------------------
+ * replaces the per-atom scan `omega_k = X[k, :] != 0`, ksvd.py:111.
+ * rowptr (K+1) int32; entries (N*k) int32, entry = i*k + slot, ascending inside each atom
+ * (deterministic).  Slots with idx < 0 or val == 0 are not users (ksvd.py:111). */
+LYS_API size_t lys_atom_csr_workspace_bytes(int K, int64_t N, int k);
+LYS_API int lys_build_atom_csr(const int32_t* idx, const float* val, int64_t N, int k, int K,
+                       int32_t* rowptr, int32_t* entries,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K7-K9: approximate K-SVD sweep -----------------------------------------------------
+ * replaces the atom loop of approx_ksvd, ksvd.py:105-124: sequentially for every atom,
+ * d <- normalize(R_k x_k^T) (:116-119), x_k <- R_k^T d (:121), residual refresh (:123),
+ * with R_k never materialised (R_k = R[:,users] + d x).  D (n,K) row-major and val are
+ * updated IN PLACE as in the reference; R (N,n) is the residual from lys_residual and is
+ * kept current.  unused (K) int32 receives 1 for atoms without users (:112-115).
+ * `comm` is NULL for one GPU, or a handle from lys_comm_create when the signals are
+ * sharded over ranks: the per-atom (n+2)-float partial sums are then all-reduced inside the
+ * kernel through peer-mapped buffers (see below). */
+LYS_API size_t lys_ksvd_sweep_workspace_bytes(int n, int K);
+LYS_API int lys_approx_ksvd_sweep(float* R, float* D, int64_t ldd,
+                          const int32_t* idx, float* val,
+                          const int32_t* rowptr, const int32_t* entries,
+                          int n, int K, int64_t N, int k, int n_cycles,
+                          int32_t* unused, void* comm,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K8 / K14 helpers -------------------------------------------------------------------
+ * norm_cols: D[:,c] /= (||D[:,c]||_2 + eps), lyssa/utils/math.py:65-71 (eps = 2^-52).
+ * gather_cols: D[:,j] = X[:, cols[j]], the device half of init_dictionary
+ * (lyssa/dict_learning/utils.py:64) and of unused-atom replacement (ksvd.py:205). */
+LYS_API int lys_norm_cols(float* D, int64_t ldd, int n, int K, void* stream);
+LYS_API int lys_gather_cols(const float* X, int64_t x_feat_stride, int64_t x_sig_stride, int n,
+                    const int64_t* cols, int n_cols, float* D, int64_t ldd, const int32_t* dst_cols,
+                    void* stream);
+
+/* ---- K12/K13: online dictionary learning ------------------------------------------------
+ * accumulate: A = beta*A + Z_b Z_b^T, B = beta*B + X_b Z_b^T from sparse codes
+ * (lyssa/dict_learning/online_dict_learn.py:84-85).  A (K,K), B (n,K) row-major.
+ * With `scale_only` != 0 only the beta scaling is applied (used before a multi-rank sum).
+ * update: D <- norm_cols(clamp(D + (B - D A) diag(1/(A_kk + eps)))), :91-98 (Jacobi, stale
+ * D A; clamp only if non_neg). */
+LYS_API int lys_odl_accumulate(const float* Xb, int64_t x_feat_stride, int64_t x_sig_stride,
+                       const int32_t* idx, const float* val, int n, int K, int64_t b, int k,
+                       float beta, float* A, float* B, void* stream);
+LYS_API size_t lys_odl_update_workspace_bytes(int n, int K);
+LYS_API int lys_odl_update_dict(float* D, int64_t ldd, const float* A, const float* B, int n, int K,
+                        int non_neg, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- multi-GPU: peer-mapped exchange buffers for the sweep's per-atom all-reduce ---------
+ * One process per GPU.  Each rank creates a comm (allocates its exchange buffer), exports
+ * a 64-byte handle, the host (torch.distributed) all-gathers the handles, and every rank
+ * opens its peers'.  No reference counterpart: the reference is single-host
+ * multiprocessing (lyssa/utils/__init__.py:92-146). */
+#define LYS_COMM_HANDLE_BYTES 64
+LYS_API int lys_comm_create(int rank, int world, void** comm);
+LYS_API int lys_comm_export(void* comm, unsigned char handle[LYS_COMM_HANDLE_BYTES]);
+LYS_API int lys_comm_connect(void* comm, const unsigned char* all_handles /* world*64 bytes */);
+LYS_API int lys_comm_destroy(void* comm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LYSSA_B200_H */

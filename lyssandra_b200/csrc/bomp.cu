@@ -1,0 +1,251 @@
+// bomp.cu — C-ABI entry points of the Batch-OMP encode path (lyssa/sparse_coding.py:629-635,
+// :708-726 -> batch_omp :302-367) and the host-buffer pipeline behind
+// sparse_encoder.encode(X_numpy, D_numpy).
+#include "common.cuh"
+#include <mutex>
+#include <vector>
+#include <algorithm>
+
+namespace lys {
+
+int bomp_greedy_generic(const float* alpha, const float* G, int K, int64_t C, int k,
+                        int32_t* idx, float* val, int32_t* nsel,
+                        float* Z, int64_t zas, int64_t zss, cudaStream_t stream);
+
+// fused tcgen05 path (bomp_fused.cu); returns LYS_EUNSUPPORTED for shapes it is not built for
+int bomp_encode_fused(const float* X, int64_t xfs, int64_t xss, const float* D, int64_t ldd,
+                      const float* G, int n, int K, int64_t N, int k,
+                      int32_t* idx, float* val, int32_t* nsel,
+                      float* Z, int64_t zas, int64_t zss,
+                      void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t bomp_fused_workspace_bytes(int n, int K, int64_t N, int k);
+
+namespace {
+
+// signals per correlation chunk of the generic path: the (chunk x K) fp32 Alpha tile is
+// written by the GEMM and read once by the greedy kernel; 16384 x 1024 x 4 B = 64 MB stays
+// inside the 126 MB L2, so Alpha costs (almost) no HBM traffic.
+constexpr int64_t kChunkBytesTarget = 64ll << 20;
+
+int64_t generic_chunk(int K, int64_t N)
+{
+    int64_t c = kChunkBytesTarget / ((int64_t)K * 4);
+    c = std::max<int64_t>(1024, c / 1024 * 1024);
+    return std::min<int64_t>(c, std::max<int64_t>(N, 1));
+}
+
+__global__ void dense_fill_kernel(const int32_t* __restrict__ idx, const float* __restrict__ val,
+                                  int64_t N, int k, int K, float* __restrict__ Z,
+                                  int64_t zas, int64_t zss)
+{
+    // one warp per signal: zero the dense row/column, then scatter the k coefficients
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = w; i < N; i += nw) {
+        float* z = Z + i * zss;
+        if (zas == 1 && (K % 4) == 0 && ((reinterpret_cast<uintptr_t>(z) & 15) == 0)) {
+            float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int c = lane * 4; c < K; c += 128) *reinterpret_cast<float4*>(z + c) = zero;
+        } else {
+            for (int c = lane; c < K; c += 32) z[(int64_t)c * zas] = 0.f;
+        }
+        __syncwarp();
+        if (lane < k) {
+            int a = idx[i * k + lane];
+            if (a >= 0) z[(int64_t)a * zas] = val[i * k + lane];
+        }
+    }
+}
+
+}  // namespace
+}  // namespace lys
+
+using namespace lys;
+
+extern "C" size_t lys_bomp_workspace_bytes(int n, int K, int64_t N, int k)
+{
+    if (n < 1 || K < 1 || N < 0 || k < 1) return 0;
+    size_t generic = (size_t)generic_chunk(K, N) * (size_t)K * sizeof(float) + 256;
+    size_t fused = bomp_fused_workspace_bytes(n, K, N, k);
+    return std::max(generic, fused);
+}
+
+extern "C" int lys_bomp_encode(const float* X, int64_t xfs, int64_t xss,
+                               const float* D, int64_t ldd, const float* G,
+                               int n, int K, int64_t N, int k,
+                               int32_t* idx, float* val, int32_t* nsel,
+                               float* Z, int64_t zas, int64_t zss,
+                               void* workspace, size_t workspace_bytes, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LYS_CHECK_ARG(n >= 1 && n <= LYS_MAX_FEATURES, "lys_bomp_encode: n=%d out of range [1,%d]", n, LYS_MAX_FEATURES);
+    LYS_CHECK_ARG(K >= 1 && K <= LYS_MAX_ATOMS, "lys_bomp_encode: K=%d out of range [1,%d]", K, LYS_MAX_ATOMS);
+    LYS_CHECK_ARG(k >= 1 && k <= LYS_MAX_NONZERO && k <= K,
+                  "lys_bomp_encode: n_nonzero_coefs=%d must be in [1, min(K=%d, %d)]", k, K, LYS_MAX_NONZERO);
+    LYS_CHECK_ARG(N >= 0, "lys_bomp_encode: N < 0");
+    if (N == 0) return LYS_OK;
+    LYS_CHECK_ARG(X && D && G && idx && val, "lys_bomp_encode: null pointer");
+    LYS_CHECK_ARG(ldd >= K, "lys_bomp_encode: ldd < K");
+    LYS_CHECK_ARG(!Z || (zas >= 1 && zss >= 1), "lys_bomp_encode: bad Z strides");
+    LYS_CHECK_ARG(workspace != nullptr, "lys_bomp_encode: workspace is null");
+    if (workspace_bytes < lys_bomp_workspace_bytes(n, K, N, k)) {
+        set_error("lys_bomp_encode: workspace %zu B < required %zu B", workspace_bytes,
+                  lys_bomp_workspace_bytes(n, K, N, k));
+        return LYS_EWORKSPACE;
+    }
+
+    int rc = bomp_encode_fused(X, xfs, xss, D, ldd, G, n, K, N, k, idx, val, nsel, Z, zas, zss,
+                               workspace, workspace_bytes, stream);
+    if (rc != LYS_EUNSUPPORTED) return rc;
+
+    // generic path: per chunk, Alpha = X_chunk^T D (fp32 GEMM) then one warp per signal
+    float* alpha = reinterpret_cast<float*>(workspace);
+    const int64_t chunk = generic_chunk(K, N);
+    for (int64_t s0 = 0; s0 < N; s0 += chunk) {
+        const int64_t C = std::min(chunk, N - s0);
+        rc = sgemm_strided(X + s0 * xss, xss, xfs, D, ldd, 1, alpha, K, 1, C, K, n, stream);
+        if (rc) return rc;
+        rc = bomp_greedy_generic(alpha, G, K, C, k, idx + s0 * k, val + s0 * k,
+                                 nsel ? nsel + s0 : nullptr,
+                                 Z ? Z + s0 * zss : nullptr, zas, zss, stream);
+        if (rc) return rc;
+    }
+    return LYS_OK;
+}
+
+extern "C" int lys_codes_to_dense(const int32_t* idx, const float* val, int64_t N, int k, int K,
+                                  float* Z, int64_t zas, int64_t zss, void* stream)
+{
+    LYS_CHECK_ARG(idx && val && Z, "lys_codes_to_dense: null pointer");
+    LYS_CHECK_ARG(k >= 1 && k <= LYS_MAX_NONZERO && K >= 1 && N >= 0, "lys_codes_to_dense: bad shape");
+    if (N == 0) return LYS_OK;
+    int64_t blocks = std::min<int64_t>((N + 7) / 8, (int64_t)sm_count() * 8);
+    dense_fill_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(idx, val, N, k, K, Z, zas, zss);
+    LYS_LAUNCH_CHECK("dense_fill_kernel");
+    return LYS_OK;
+}
+
+// --------------------------------------------------------------------------- host pipeline
+namespace {
+
+struct HostPipe {
+    int device = -1;
+    size_t bytes = 0;
+    unsigned char* base = nullptr;
+    cudaStream_t streams[2] = {nullptr, nullptr};
+};
+std::mutex g_pipe_mu;
+std::vector<HostPipe> g_pipes;
+
+HostPipe* get_pipe(int device, size_t bytes)
+{
+    for (auto& p : g_pipes)
+        if (p.device == device) {
+            if (p.bytes < bytes) {
+                cudaFree(p.base); p.base = nullptr; p.bytes = 0;
+                if (cudaMalloc(&p.base, bytes) != cudaSuccess) return nullptr;
+                p.bytes = bytes;
+            }
+            return &p;
+        }
+    HostPipe p; p.device = device;
+    if (cudaMalloc(&p.base, bytes) != cudaSuccess) return nullptr;
+    p.bytes = bytes;
+    for (int s = 0; s < 2; ++s)
+        if (cudaStreamCreateWithFlags(&p.streams[s], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    g_pipes.push_back(p);
+    return &g_pipes.back();
+}
+
+}  // namespace
+
+extern "C" int lys_bomp_encode_host(const float* X, int64_t xfs, int64_t xss,
+                                    const float* D, int64_t ldd,
+                                    int n, int K, int64_t N, int k,
+                                    int32_t* idx, float* val, int32_t* nsel,
+                                    float* Z, int64_t zas, int64_t zss, int device)
+{
+    LYS_CHECK_ARG(X && D, "lys_bomp_encode_host: null input");
+    LYS_CHECK_ARG(n >= 1 && n <= LYS_MAX_FEATURES && K >= 1 && K <= LYS_MAX_ATOMS && ldd >= K,
+                  "lys_bomp_encode_host: bad dictionary shape");
+    LYS_CHECK_ARG(k >= 1 && k <= LYS_MAX_NONZERO && k <= K, "lys_bomp_encode_host: bad n_nonzero_coefs=%d", k);
+    LYS_CHECK_ARG((xfs == 1 && xss >= n) || (xss == 1 && xfs >= N),
+                  "lys_bomp_encode_host: X must be signal-major (feat stride 1) or feature-major (signal stride 1)");
+    LYS_CHECK_ARG(!Z || (zas == 1 && zss >= K) || (zss == 1 && zas >= N),
+                  "lys_bomp_encode_host: Z must be signal-major (atom stride 1) or atom-major (signal stride 1)");
+    if (N == 0) return LYS_OK;
+    std::lock_guard<std::mutex> lock(g_pipe_mu);
+    if (device >= 0) LYS_CUDA(cudaSetDevice(device));
+    else LYS_CUDA(cudaGetDevice(&device));
+
+    const int64_t chunk = std::min<int64_t>(N, 32768);
+    const size_t ws_bytes = align_up(lys_bomp_workspace_bytes(n, K, chunk, k), 256);
+    const size_t d_bytes = align_up((size_t)n * K * 4, 256), g_bytes = align_up((size_t)K * K * 4, 256);
+    const size_t x_bytes = align_up((size_t)chunk * n * 4, 256);
+    const size_t i_bytes = align_up((size_t)chunk * k * 4, 256);
+    const size_t s_bytes = align_up((size_t)chunk * 4, 256);
+    const size_t z_bytes = Z ? align_up((size_t)chunk * K * 4, 256) : 0;
+    const size_t slot_bytes = x_bytes + 2 * i_bytes + s_bytes + z_bytes + ws_bytes;
+    HostPipe* pipe = get_pipe(device, d_bytes + g_bytes + 2 * slot_bytes);
+    if (!pipe) { set_error("lys_bomp_encode_host: device allocation failed"); return LYS_ECUDA; }
+
+    unsigned char* p = pipe->base;
+    float* dD = reinterpret_cast<float*>(p); p += d_bytes;
+    float* dG = reinterpret_cast<float*>(p); p += g_bytes;
+    struct Slot { float* x; int32_t* idx; float* val; int32_t* nsel; float* z; void* ws; } slot[2];
+    for (int s = 0; s < 2; ++s) {
+        slot[s].x = reinterpret_cast<float*>(p); p += x_bytes;
+        slot[s].idx = reinterpret_cast<int32_t*>(p); p += i_bytes;
+        slot[s].val = reinterpret_cast<float*>(p); p += i_bytes;
+        slot[s].nsel = reinterpret_cast<int32_t*>(p); p += s_bytes;
+        slot[s].z = Z ? reinterpret_cast<float*>(p) : nullptr; p += z_bytes;
+        slot[s].ws = p; p += ws_bytes;
+    }
+    cudaStream_t s0 = pipe->streams[0], s1 = pipe->streams[1];
+    LYS_CUDA(cudaMemcpy2DAsync(dD, (size_t)K * 4, D, (size_t)ldd * 4, (size_t)K * 4, n, cudaMemcpyHostToDevice, s0));
+    int rc = lys_gram(dD, K, n, K, dG, s0);
+    if (rc) return rc;
+    cudaEvent_t ready;
+    LYS_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    LYS_CUDA(cudaEventRecord(ready, s0));
+    LYS_CUDA(cudaStreamWaitEvent(s1, ready, 0));
+
+    const bool x_sig_major = (xfs == 1);
+    const bool z_sig_major = (zas == 1);
+    int which = 0;
+    for (int64_t c0 = 0; c0 < N; c0 += chunk, which ^= 1) {
+        const int64_t C = std::min(chunk, N - c0);
+        cudaStream_t st = pipe->streams[which];
+        Slot& sl = slot[which];
+        int64_t dxfs, dxss;
+        if (x_sig_major) {       // host rows of n floats, row stride xss -> device (C, n)
+            LYS_CUDA(cudaMemcpy2DAsync(sl.x, (size_t)n * 4, X + c0 * xss, (size_t)xss * 4, (size_t)n * 4, C,
+                                       cudaMemcpyHostToDevice, st));
+            dxfs = 1; dxss = n;
+        } else {                 // host (n, N) feature-major -> device (n, C)
+            LYS_CUDA(cudaMemcpy2DAsync(sl.x, (size_t)C * 4, X + c0, (size_t)xfs * 4, (size_t)C * 4, n,
+                                       cudaMemcpyHostToDevice, st));
+            dxfs = C; dxss = 1;
+        }
+        int64_t dzas = z_sig_major ? 1 : C, dzss = z_sig_major ? K : 1;
+        rc = lys_bomp_encode(sl.x, dxfs, dxss, dD, K, dG, n, K, C, k, sl.idx, sl.val, sl.nsel,
+                             sl.z, dzas, dzss, sl.ws, ws_bytes, st);
+        if (rc) return rc;
+        if (idx) LYS_CUDA(cudaMemcpyAsync(idx + c0 * k, sl.idx, (size_t)C * k * 4, cudaMemcpyDeviceToHost, st));
+        if (val) LYS_CUDA(cudaMemcpyAsync(val + c0 * k, sl.val, (size_t)C * k * 4, cudaMemcpyDeviceToHost, st));
+        if (nsel) LYS_CUDA(cudaMemcpyAsync(nsel + c0, sl.nsel, (size_t)C * 4, cudaMemcpyDeviceToHost, st));
+        if (Z) {
+            if (z_sig_major)
+                LYS_CUDA(cudaMemcpy2DAsync(Z + c0 * zss, (size_t)zss * 4, sl.z, (size_t)K * 4, (size_t)K * 4, C,
+                                           cudaMemcpyDeviceToHost, st));
+            else
+                LYS_CUDA(cudaMemcpy2DAsync(Z + c0, (size_t)zas * 4, sl.z, (size_t)C * 4, (size_t)C * 4, K,
+                                           cudaMemcpyDeviceToHost, st));
+        }
+    }
+    LYS_CUDA(cudaStreamSynchronize(s0));
+    LYS_CUDA(cudaStreamSynchronize(s1));
+    cudaEventDestroy(ready);
+    return LYS_OK;
+}

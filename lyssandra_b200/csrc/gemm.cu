@@ -1,0 +1,113 @@
+// gemm.cu — strided fp32 SIMT GEMM for the SMALL dense contractions of the path:
+//   K1  Gram = D^T D            (lyssa/sparse_coding.py:630)      134 MFLOP, once per encode
+//   K13 DA   = D A              (lyssa/dict_learning/online_dict_learn.py:91)
+// and the correlation Alpha = X^T D of the generic-shape encode path (sparse_coding.py:631).
+// fp32 FFMA with a fixed p = 0..Kd-1 accumulation order per output element (deterministic,
+// fp32-faithful: the argmax decisions of Batch-OMP are sensitive to ~1e-6 relative error in
+// Alpha, SURVEY.md §7 hard part 1, so no single-pass TF32/BF16 here).
+#include "common.cuh"
+
+namespace lys {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 8, TM = 8, TN = 8, NT = 256;
+
+__global__ void __launch_bounds__(NT)
+sgemm_kernel(const float* __restrict__ A, int64_t sai, int64_t sap,
+             const float* __restrict__ B, int64_t sbp, int64_t sbj,
+             float* __restrict__ C, int64_t sci, int64_t scj,
+             int64_t M, int64_t Nc, int Kd)
+{
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int t = threadIdx.x;
+    const int64_t i0 = (int64_t)blockIdx.y * BM;
+    const int64_t j0 = (int64_t)blockIdx.x * BN;
+    const int ty = t / 16, tx = t % 16;      // 16 x 16 threads, each 8 x 8 outputs
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int a = 0; a < TM; ++a)
+#pragma unroll
+        for (int b = 0; b < TN; ++b) acc[a][b] = 0.f;
+
+    const bool a_p_contig = (sap == 1);
+    const bool b_j_contig = (sbj == 1);
+
+    for (int p0 = 0; p0 < Kd; p0 += BK) {
+#pragma unroll
+        for (int e = 0; e < (BM * BK) / NT; ++e) {
+            int id = t + e * NT;
+            int i, p;
+            if (a_p_contig) { i = id / BK; p = id % BK; } else { i = id % BM; p = id / BM; }
+            int64_t gi = i0 + i; int gp = p0 + p;
+            As[p][i] = (gi < M && gp < Kd) ? A[gi * sai + gp * sap] : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < (BN * BK) / NT; ++e) {
+            int id = t + e * NT;
+            int j, p;
+            if (b_j_contig) { j = id % BN; p = id / BN; } else { p = id % BK; j = id / BK; }
+            int64_t gj = j0 + j; int gp = p0 + p;
+            Bs[p][j] = (gj < Nc && gp < Kd) ? B[gp * sbp + gj * sbj] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < BK; ++p) {
+            float av[TM], bv[TN];
+#pragma unroll
+            for (int a = 0; a < TM; a += 4) {
+                float4 v = *reinterpret_cast<const float4*>(&As[p][ty * 4 + a * 16]);
+                av[a] = v.x; av[a + 1] = v.y; av[a + 2] = v.z; av[a + 3] = v.w;
+            }
+#pragma unroll
+            for (int b = 0; b < TN; b += 4) {
+                float4 v = *reinterpret_cast<const float4*>(&Bs[p][tx * 4 + b * 16]);
+                bv[b] = v.x; bv[b + 1] = v.y; bv[b + 2] = v.z; bv[b + 3] = v.w;
+            }
+#pragma unroll
+            for (int a = 0; a < TM; ++a)
+#pragma unroll
+                for (int b = 0; b < TN; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+        }
+        __syncthreads();
+    }
+    // rows: ty*4 + {0..3} and 64 + ty*4 + {0..3}; cols likewise with tx
+#pragma unroll
+    for (int a = 0; a < TM; ++a) {
+        int64_t gi = i0 + ty * 4 + (a / 4) * 64 + (a % 4);
+        if (gi >= M) continue;
+#pragma unroll
+        for (int b = 0; b < TN; ++b) {
+            int64_t gj = j0 + tx * 4 + (b / 4) * 64 + (b % 4);
+            if (gj < Nc) C[gi * sci + gj * scj] = acc[a][b];
+        }
+    }
+}
+
+}  // namespace
+
+int sgemm_strided(const float* A, int64_t sai, int64_t sap,
+                  const float* B, int64_t sbp, int64_t sbj,
+                  float* C, int64_t sci, int64_t scj,
+                  int64_t M, int64_t Nc, int Kd, cudaStream_t stream)
+{
+    if (M <= 0 || Nc <= 0) return LYS_OK;
+    dim3 grid((unsigned)((Nc + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
+    if (grid.y > 65535u) { set_error("sgemm: M too large for one launch"); return LYS_EINVAL; }
+    sgemm_kernel<<<grid, NT, 0, stream>>>(A, sai, sap, B, sbp, sbj, C, sci, scj, M, Nc, Kd);
+    LYS_LAUNCH_CHECK("sgemm_kernel");
+    return LYS_OK;
+}
+
+}  // namespace lys
+
+extern "C" int lys_gram(const float* D, int64_t ldd, int n, int K, float* G, void* stream)
+{
+    LYS_CHECK_ARG(D && G, "lys_gram: null pointer");
+    LYS_CHECK_ARG(n >= 1 && n <= LYS_MAX_FEATURES && K >= 1 && K <= LYS_MAX_ATOMS && ldd >= K,
+                  "lys_gram: bad shape n=%d K=%d ldd=%lld", n, K, (long long)ldd);
+    // G(i,j) = sum_f D[f][i] D[f][j]
+    return lys::sgemm_strided(D, 1, ldd, D, ldd, 1, G, K, 1, K, K, n, (cudaStream_t)stream);
+}

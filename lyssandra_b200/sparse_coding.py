@@ -1,0 +1,122 @@
+"""Mirror of ``lyssa.sparse_coding.sparse_encoder`` for the Batch-OMP hot path
+(/root/reference/lyssa/sparse_coding.py:587-603 constructor + encode/__call__,
+:629-635 the 'bomp' branch, :706 the unknown-algorithm error, :708-726 dispatch).
+
+Only ``algorithm='bomp'`` runs — on the GPU, through liblyssa_b200.so.  The reference's other
+coders are outside this engine's scope and raise NotImplementedError rather
+than silently running on the CPU; an unknown name raises ValueError exactly like the
+reference.  The public attributes (algorithm, params, n_jobs, verbose, mmap, name) are plain
+and mutable because reference callers mutate them (ksvd.py:159, online_dict_learn.py:41).
+"""
+from __future__ import annotations
+
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import torch
+
+from . import engine
+
+_REFERENCE_ALGORITHMS = ("omp", "bomp", "thresh", "nnomp", "group_omp", "sparse_group_omp",
+                         "somp", "iht", "lasso", "llc")
+
+
+class sparse_encoder(object):
+    """sparse_encoder(algorithm, params, n_jobs, verbose, mmap, name) — same signature and
+    defaults as the reference (sparse_coding.py:587).
+
+    encode(X, D) / __call__(X, D): X (n_features, n_samples), D (n_features, n_atoms) ->
+    Z (n_atoms, n_samples), float32.
+      * torch CUDA tensors in  -> torch CUDA tensor out (a transposed view of signal-major
+        storage; no host round trip);
+      * NumPy arrays / CPU tensors in -> NumPy array out, through the library's overlapped
+        host pipeline.  ``n_jobs`` > 1 (or -1 = all, sparse_coding.py:594-595) spreads
+        contiguous column blocks over that many visible GPUs, the analogue of run_parallel's
+        contiguous batches (lyssa/utils/__init__.py:93-97,166-180).
+    encode_sparse(X, D) returns engine.SparseCodes (idx, val, nsel) without densifying — what
+    the learners in lyssandra_b200.dict_learning consume.
+    """
+
+    def __init__(self, algorithm="omp", params=None, n_jobs=1, verbose=True, mmap=False, name="sparse_coder"):
+        self.name = name
+        self.algorithm = algorithm
+        self.params = params
+        if self.params is None:
+            self.params = {}
+        if n_jobs == -1:
+            n_jobs = max(torch.cuda.device_count(), 1)
+        self.n_jobs = n_jobs
+        self.verbose = verbose
+        self.mmap = mmap
+
+    # ------------------------------------------------------------------ reference surface
+    def encode(self, X, D):
+        return self.__call__(X, D)
+
+    def __call__(self, X, D):
+        k = self._check()
+        if torch.is_tensor(X) and X.is_cuda:
+            Dd = engine.as_dictionary(D, X.device)
+            Xd = engine.as_device_matrix(X, X.device)
+            _, Z = engine.bomp_encode(Xd, Dd, k, dense=True)
+            return Z
+        Xh, Dh = self._host_arrays(X, D)
+        return self._encode_host(Xh, Dh, k, dense=True)[3]
+
+    # ------------------------------------------------------------------------ extensions
+    def encode_sparse(self, X, D, G=None):
+        """Device-resident sparse codes; X/D may be NumPy (uploaded) or CUDA tensors."""
+        k = self._check()
+        Xd = engine.as_device_matrix(X, X.device if torch.is_tensor(X) and X.is_cuda else None)
+        Dd = engine.as_dictionary(D, Xd.device)
+        return engine.bomp_encode(Xd, Dd, k, G=G, dense=False)
+
+    def encode_sparse_host(self, X, D):
+        """NumPy in, NumPy (idx, val, nsel) out — no dense Z crosses PCIe."""
+        k = self._check()
+        Xh, Dh = self._host_arrays(X, D)
+        idx, val, nsel, _ = self._encode_host(Xh, Dh, k, dense=False)
+        return idx, val, nsel
+
+    # --------------------------------------------------------------------------- helpers
+    def _check(self):
+        if self.algorithm != "bomp":
+            if self.algorithm in _REFERENCE_ALGORITHMS:
+                raise NotImplementedError(
+                    "algorithm %r is outside the B200 engine's scope: only 'bomp' is implemented "
+                    "(no CPU fallback by design)" % (self.algorithm,))
+            raise ValueError("Sparse optimizer not found.")          # sparse_coding.py:706
+        k = self.params.get("n_nonzero_coefs")
+        if k is None:
+            # the reference crashes inside np.zeros((None, None)) (sparse_coding.py:317, quirk Q2)
+            raise ValueError("params['n_nonzero_coefs'] must be set for algorithm 'bomp'")
+        return int(k)
+
+    @staticmethod
+    def _host_arrays(X, D):
+        Xh = X.detach().cpu().numpy() if torch.is_tensor(X) else np.asarray(X)
+        Dh = D.detach().cpu().numpy() if torch.is_tensor(D) else np.asarray(D)
+        if Xh.ndim != 2 or Dh.ndim != 2:
+            raise ValueError("X and D must be 2-D (features x columns)")
+        return Xh, Dh
+
+    def _encode_host(self, Xh, Dh, k, dense):
+        n_gpus = min(int(self.n_jobs), max(torch.cuda.device_count(), 1)) if self.n_jobs and self.n_jobs > 1 else 1
+        N = Xh.shape[1]
+        if n_gpus <= 1 or N < 2 * n_gpus:
+            return engine.bomp_encode_host(Xh, Dh, k, dense=dense)
+        K = Dh.shape[1]
+        bounds = np.linspace(0, N, n_gpus + 1).astype(np.int64)
+        Xh = np.ascontiguousarray(Xh, dtype=np.float32) if not (Xh.strides[0] == 4 or Xh.strides[1] == 4) else Xh
+
+        def work(g):
+            lo, hi = int(bounds[g]), int(bounds[g + 1])
+            return engine.bomp_encode_host(Xh[:, lo:hi], Dh, k, dense=dense, device=g)
+
+        with ThreadPoolExecutor(max_workers=n_gpus) as ex:
+            parts = list(ex.map(work, range(n_gpus)))
+        idx = np.concatenate([p[0] for p in parts], axis=0)
+        val = np.concatenate([p[1] for p in parts], axis=0)
+        nsel = np.concatenate([p[2] for p in parts], axis=0)
+        Z = np.concatenate([p[3] for p in parts], axis=1) if dense else None
+        return idx, val, nsel, Z

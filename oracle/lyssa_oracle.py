@@ -1,0 +1,381 @@
+"""TEST INFRASTRUCTURE ONLY — CPU (NumPy, float64) restatement of the reference's hot path.
+
+This is the *checker*: only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs may import it.  The product path
+(``lyssandra_b200``) never does, and fails loudly when its CUDA library is missing.
+
+Parity status: **pinned against the reference itself.**  The reference (Python 2, no tests
+with numbers — SURVEY.md §4) is executed in the build container by ``oracle/ref_loader.py``
+(in-memory py3 token edits only) and this restatement is compared with it bit-for-bit /
+to 1e-12 in ``tests/test_oracle_vs_reference.py`` and through the committed fixtures
+``tests/golden/*.npz`` written by ``oracle/gen_golden.py``.
+
+Every function cites the reference lines it follows (paths relative to /root/reference).
+All arithmetic is float64 exactly as in the reference ("datapoints in columns").
+"""
+from __future__ import annotations
+
+import itertools
+import multiprocessing
+import os
+
+import numpy as np
+from scipy.linalg import solve_triangular
+
+F64_EPS = np.finfo(float).eps
+
+
+# --------------------------------------------------------------------------- utils/math.py
+def normalize(x, eps=F64_EPS):
+    """x / (||x||_2 + eps) — lyssa/utils/math.py:61-62 (zero vector -> zeros, never NaN)."""
+    x = np.asarray(x, dtype=float)
+    return x / (np.sqrt(np.dot(x, x)) + eps)
+
+
+def norm_cols(M, eps=F64_EPS):
+    """In-place column normalisation with the +eps convention — lyssa/utils/math.py:65-71."""
+    scale = np.sqrt(np.einsum("ij,ij->j", M, M)) + eps
+    M /= scale[np.newaxis, :]
+    return M
+
+
+def frobenius_squared(M):
+    """sum(M**2) — lyssa/utils/math.py:57-58."""
+    return np.sum(np.power(M, 2))
+
+
+# ----------------------------------------------------------------------- utils/__init__.py
+def gen_even_batches(n_items, n_batches):
+    """n_batches contiguous ranges, the last one takes the remainder —
+    lyssa/utils/__init__.py:166-180 (n_items < n_batches -> leading empty ranges, quirk Q8)."""
+    width = int(np.floor(n_items / float(n_batches)))
+    bounds = [(b * width, (b + 1) * width) for b in range(n_batches - 1)]
+    bounds.append(((n_batches - 1) * width, n_items))
+    return [range(lo, hi) for lo, hi in bounds]
+
+
+def gen_batches(n_items, batch_size=None):
+    """Fixed-size contiguous ranges + one short tail — lyssa/utils/__init__.py:183-201."""
+    if batch_size is None:
+        return [range(0, n_items)]
+    full = int(np.floor(n_items / float(batch_size)))
+    out = [range(b * batch_size, (b + 1) * batch_size) for b in range(full)]
+    if n_items > full * batch_size:
+        out.append(range(full * batch_size, n_items))
+    return out
+
+
+# ------------------------------------------------------------------------ sparse_coding.py
+def batch_omp(X, Alpha, D, Gram, n_nonzero_coefs=None, tol=None, trace=None):
+    """Batch-OMP over the columns of Alpha — lyssa/sparse_coding.py:302-367.
+
+    Per signal: greedy argmax of |a| (first maximum wins, :322); stop if the atom is
+    already selected (:323-325); incremental Cholesky row by forward substitution with a
+    *literal 1* for the atom self-product (:330-349, quirk Q1) and stop when
+    1 - w.w < eps (:335,:345); coefficients by two triangular solves (:353-354);
+    a = a0 - G[:, I] z (:359).  ``tol`` is accepted and ignored (:302,:536).  X and D are
+    not read (as in the reference).
+
+    ``trace`` (optional dict) receives per-signal decision margins used by the parity tests'
+    near-tie policy: 'gap' (N,k) relative top1-top2 gap of |a| at each executed step,
+    'vs' (N,k) the Cholesky pivot 1 - w.w, 'nsel' (N,) number of selected atoms.
+    """
+    n_atoms, n_signals = Alpha.shape
+    k_max = n_nonzero_coefs
+    Z = np.zeros((n_atoms, n_signals))
+    if trace is not None:
+        trace["gap"] = np.full((n_signals, k_max), np.inf)
+        trace["vs"] = np.full((n_signals, k_max), 1.0)
+        trace["nsel"] = np.zeros(n_signals, dtype=int)
+
+    for i in range(n_signals):
+        support = np.array([]).astype(int)
+        a0 = Alpha[:, i]
+        a = a0
+        L = np.zeros((k_max, k_max))
+        for j in range(k_max):
+            mag = np.abs(a)
+            pick = np.argmax(mag)                                    # :322
+            if trace is not None:
+                top = mag[pick]
+                mag2 = mag.copy(); mag2[pick] = -1.0
+                trace["gap"][i, j] = (top - mag2.max()) / top if top > 0 else 0.0
+            if pick in support:                                      # :323-325
+                break
+            g = Gram[support, pick]                                  # :327
+            if j == 0:                                               # :360-363
+                support = np.append(support, pick)
+                z = a0[support]
+                a = a0 - np.dot(Gram[:, support], z)
+                continue
+            if j == 1:                                               # :330-338
+                w = g[0]
+                pivot = 1 - w * w
+                if trace is not None:
+                    trace["vs"][i, j] = pivot
+                if pivot < F64_EPS:
+                    break
+                L[:2, :2] = [[1, 0], [w, np.sqrt(pivot)]]
+            else:                                                    # :340-349
+                w = solve_triangular(L[:j, :j], g, lower=True, check_finite=False)
+                pivot = 1 - np.dot(w, w)
+                if trace is not None:
+                    trace["vs"][i, j] = pivot
+                if pivot < F64_EPS:
+                    break
+                L[j, :j] = w
+                L[j, j] = np.sqrt(pivot)
+            support = np.append(support, pick)                       # :351
+            y = solve_triangular(L[:j + 1, :j + 1], a0[support], lower=True)          # :353
+            z = solve_triangular(L[:j + 1, :j + 1], y, trans=1, lower=True)           # :354
+            a = a0 - np.dot(Gram[:, support], z)                     # :359
+        Z[support, i] = z                                            # :365
+        if trace is not None:
+            trace["nsel"][i] = len(support)
+    return Z
+
+
+def _bomp_job(args):
+    alpha_cols, gram, k = args
+    return batch_omp(None, alpha_cols, None, gram, n_nonzero_coefs=k)
+
+
+def _single_thread_blas():
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:  # pragma: no cover
+        pass
+
+
+class sparse_encoder(object):
+    """The 'bomp' branch of lyssa.sparse_coding.sparse_encoder — sparse_coding.py:587-603,
+    :629-635 (Gram, Alpha, partial(batch_omp)), :708-726 (run_parallel with n_batches=100).
+    Unknown algorithms raise ValueError (:706).  Only what the hot path needs is restated:
+    'bomp' (and nothing else); n_jobs>1 reproduces run_parallel's regime — a process pool
+    over 100 contiguous column batches with one BLAS thread per worker
+    (lyssa/utils/__init__.py:92-146, sparse_coding.py:713-716)."""
+
+    def __init__(self, algorithm="omp", params=None, n_jobs=1, verbose=True, mmap=False, name="sparse_coder"):
+        self.name = name
+        self.algorithm = algorithm
+        self.params = {} if params is None else params
+        if n_jobs == -1:
+            n_jobs = multiprocessing.cpu_count()
+        self.n_jobs = n_jobs
+        self.verbose = verbose
+        self.mmap = mmap
+
+    def encode(self, X, D):
+        return self.__call__(X, D)
+
+    def __call__(self, X, D):
+        if self.algorithm != "bomp":
+            if self.algorithm in ("omp", "thresh", "nnomp", "group_omp", "sparse_group_omp",
+                                  "somp", "iht", "lasso", "llc"):
+                raise NotImplementedError("oracle restates only the 'bomp' hot path")
+            raise ValueError("Sparse optimizer not found.")
+        k = self.params.get("n_nonzero_coefs")
+        n_atoms, n_signals = D.shape[1], X.shape[1]
+        gram = np.dot(D.T, D)                                        # :630
+        alpha = np.dot(D.T, X)                                       # :631
+        if self.n_jobs == 1:                                         # utils/__init__.py:78-90
+            Z = np.zeros((n_atoms, n_signals))
+            Z[:] = batch_omp(X, alpha, D, gram, n_nonzero_coefs=k, tol=self.params.get("tol"))
+            return Z
+        Z = np.zeros((n_atoms, n_signals))
+        parts = gen_even_batches(n_signals, 100)                     # :93-97
+        ctx = multiprocessing.get_context("fork")
+        with ctx.Pool(processes=self.n_jobs, initializer=_single_thread_blas) as pool:
+            jobs = [(alpha[:, r.start:r.stop], gram, k) for r in parts]
+            for r, out in zip(parts, pool.imap(_bomp_job, jobs)):
+                Z[:, r.start:r.stop] = out                           # :138-146
+        return Z
+
+
+# ------------------------------------------------------------------ dict_learning/utils.py
+def approx_error(D, Z, X, n_jobs=1):
+    """||X - D Z||_F^2 — lyssa/dict_learning/utils.py:14-19."""
+    return frobenius_squared(X - np.dot(D, Z))
+
+
+def average_mutual_coherence(D):
+    """mean off-diagonal |D^T D| — lyssa/dict_learning/utils.py:7-11."""
+    K = D.shape[1]
+    C = np.abs(np.dot(D.T, D))
+    np.fill_diagonal(C, 0)
+    return np.sum(C) / float(K * (K - 1))
+
+
+def init_dictionary(X, n_atoms, method="data", return_unused_data=False, normalize=True):
+    """method='data' — lyssa/dict_learning/utils.py:49-70: candidate columns have
+    sum(x^2) > 1e-6 (:55); ``np.random.choice(len(cands), n_atoms, replace=False)`` on the
+    GLOBAL NumPy RNG (:61, quirk Q9); fancy-index copy (:64); norm_cols (:65-66); the
+    unused candidates come back as a Python list (:67-70)."""
+    if method != "data":
+        raise NotImplementedError("oracle restates only method='data'")
+    n_signals = X.shape[1]
+    cands = [i for i in range(n_signals) if np.sum(X[:, i] ** 2) > 1e-6]
+    if len(cands) < n_atoms:
+        raise ValueError("not enough datapoints to initialize the dictionary")
+    chosen = np.random.choice(len(cands), size=n_atoms, replace=False)
+    chosen_cols = np.array(cands).astype(int)[chosen]
+    D = X[:, chosen_cols]
+    if normalize:
+        D = norm_cols(D)
+    if return_unused_data:
+        taken = set(chosen_cols)
+        return D, [c for c in cands if c not in taken]
+    return D
+
+
+# ------------------------------------------------------------------- dict_learning/ksvd.py
+def approx_ksvd(Y, D, X, n_cycles=1, verbose=False):
+    """Approximate K-SVD sweep, sequential over atoms, D and X mutated IN PLACE —
+    lyssa/dict_learning/ksvd.py:98-126.  R = Y - D X (:103); per atom: users = X[k]!=0
+    (:111), unused atoms recorded and skipped (:112-115), Rk = R[:,users] + d x (:116),
+    d <- normalize(Rk x) (:118-119), x <- Rk^T d (:121), R[:,users] = Rk - d x (:123)."""
+    n_atoms = D.shape[1]
+    unused = []
+    R = Y - np.dot(D, X)
+    for _ in range(n_cycles):
+        for k in range(n_atoms):
+            users = X[k, :] != 0
+            if not np.any(users):
+                unused.append(k)
+                continue
+            Rk = R[:, users] + np.outer(D[:, k], X[k, users])
+            D[:, k] = np.dot(Rk, X[k, users])
+            D[:, k] = normalize(D[:, k])
+            X[k, users] = np.dot(Rk.T, D[:, k])
+            R[:, users] = Rk - np.outer(D[:, k], X[k, users])
+    return D, X, unused
+
+
+def ksvd_dict_learn(X, n_atoms, init_dict="data", sparse_coder=None, max_iter=20, non_neg=False,
+                    approx=False, eta=None, n_cycles=1, n_jobs=1, mmap=False, verbose=True,
+                    history=None):
+    """Outer K-SVD loop — lyssa/dict_learning/ksvd.py:129-231 (approx=True branch only).
+    Mirrors: array init_dict is copied (:155); encode (:177); sweep (:186); unused-atom
+    replacement by ``np.random.choice(unused_data, size=1)`` + normalize (:199-207);
+    approx_error (:220); the patience rule exactly as written, including quirk Q3
+    (error_prev only advances when verbose, :222-229).  ``history`` (list) collects the
+    per-iteration error."""
+    if not approx or non_neg or eta is not None:
+        raise NotImplementedError("oracle restates only approx=True, non_neg=False, eta=None")
+    unused_data = []
+    if isinstance(init_dict, str) and init_dict == "data":
+        D, unused_data = init_dictionary(X, n_atoms, method=init_dict, return_unused_data=True)
+    else:
+        D = np.copy(init_dict)
+    Z = np.zeros((n_atoms, X.shape[1]))
+    max_patience = 10
+    error_curr = 0
+    error_prev = 0
+    it = 0
+    patience = 0
+    while it < max_iter and patience < max_patience:
+        Z = sparse_coder(X, D)
+        D, _, unused_atoms = approx_ksvd(X, D, Z, n_cycles=n_cycles)
+        for slot in unused_atoms:
+            if len(unused_data) == 0:
+                break
+            col = np.random.choice(unused_data, size=1)[0]
+            D[:, slot] = X[:, col]
+            D[:, slot] = normalize(D[:, slot])
+            unused_data.remove(col)
+        error_curr = approx_error(D, Z, X, n_jobs=2)
+        if history is not None:
+            history.append(error_curr)
+        if verbose:
+            error_prev = error_curr
+        if (it > 0) and (error_curr > 0.9 * error_prev or error_curr > error_prev):
+            patience += 1
+        it += 1
+    return D, Z
+
+
+# ------------------------------------------------------- dict_learning/online_dict_learn.py
+def online_dict_learn(X, n_atoms, sparse_coder=None, batch_size=None, A=None, B=None, D_init=None,
+                      beta=None, n_epochs=1, verbose=False, n_jobs=1, non_neg=False, mmap=False):
+    """Mairal online dictionary learning as the reference implements it —
+    lyssa/dict_learning/online_dict_learn.py:18-124.  D_init is used WITHOUT copying (:47);
+    beta=None -> linspace(0,1,n_iter) restarted every epoch (:65-69, :79, quirk Q6);
+    A = b*A + Z Z^T, B = b*B + X Z^T (:84-85); Jacobi block update with the stale D A
+    (:91-94); optional clamp (:96-97); norm_cols (:98); end-of-epoch error + patience
+    (:101-118, same quirk as K-SVD).  Returns (D, A, B)."""
+    sparse_coder.verbose = False
+    n_features, n_signals = X.shape
+    if D_init is None:
+        D, _unused = init_dictionary(X, n_atoms, method="data", return_unused_data=True)
+    else:
+        D = D_init
+    batches = gen_batches(n_signals, batch_size=batch_size)
+    n_iter = len(batches)
+    if A is None and B is None:
+        A = np.zeros((n_atoms, n_atoms))
+        B = np.zeros((n_features, n_atoms))
+    if beta is None:
+        beta = np.linspace(0, 1, num=n_iter)
+    else:
+        beta = np.zeros(n_iter) + beta
+    max_patience = 10
+    error_prev = 0
+    patience = 0
+    for e in range(n_epochs):
+        for i, cols in zip(range(n_iter), itertools.cycle(batches)):
+            Xb = X[:, cols]
+            Zb = sparse_coder(Xb, D)
+            A = beta[i] * A + np.dot(Zb, Zb.T)
+            B = beta[i] * B + np.dot(Xb, Zb.T)
+            DA = np.dot(D, A)
+            for k in range(n_atoms):
+                D[:, k] = (1 / (A[k, k] + F64_EPS)) * (B[:, k] - DA[:, k]) + D[:, k]
+            if non_neg:
+                D[D < 0] = 0
+            D = norm_cols(D)
+        if e < n_epochs - 1:
+            if patience >= max_patience:
+                return D, A, B
+            error_curr = 0
+            for i, cols in zip(range(n_iter), itertools.cycle(batches)):
+                Xb = X[:, cols]
+                Zb = sparse_coder(Xb, D)
+                error_curr += approx_error(D, Zb, Xb, n_jobs=n_jobs)
+            if verbose:
+                error_prev = error_curr
+            if (e > 0) and (error_curr > 0.9 * error_prev or error_curr > error_prev):
+                patience += 1
+    return D, A, B
+
+
+# ------------------------------------------------------------------------- synthetic data
+def synthetic_patches(n_signals, n_features=64, seed=0):
+    """uniform [0,1) pixels, per-patch mean removed; returns float32 (n, N)
+    'datapoints in columns' as a transposed view of signal-major storage."""
+    rng = np.random.default_rng(seed)
+    P = rng.random((n_signals, n_features), dtype=np.float32)
+    P -= P.mean(axis=1, keepdims=True)
+    return P.T
+
+
+def synthetic_dictionary(n_atoms, n_features=64, seed=1):
+    """K independent draws of the same distribution, mean removed, unit-normalised with the
+    +eps convention (utils/math.py:65-71); float32 (n, K) C-contiguous."""
+    rng = np.random.default_rng(seed)
+    P = rng.random((n_atoms, n_features), dtype=np.float32)
+    P -= P.mean(axis=1, keepdims=True)
+    D = np.ascontiguousarray(P.T.astype(np.float64))
+    norm_cols(D)
+    return np.ascontiguousarray(D.astype(np.float32))
+
+
+def synthetic_descriptors(n_signals, n_features=128, seed=0):
+    """SIFT-like descriptors for cfg4: |N(0,1)| then Lowe normalisation (unit norm, clip 0.2,
+    renormalise — lyssa/feature_extract/dsift.py:146-162); float32 (n, N) view."""
+    rng = np.random.default_rng(seed)
+    P = np.abs(rng.standard_normal((n_signals, n_features), dtype=np.float32))
+    P /= np.linalg.norm(P, axis=1, keepdims=True)
+    np.minimum(P, 0.2, out=P)
+    P /= np.linalg.norm(P, axis=1, keepdims=True)
+    return P.T

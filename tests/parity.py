@@ -1,0 +1,51 @@
+"""Shared parity policy (SURVEY.md §8c "Parity definitions").
+
+Support sets must be bit-identical on every column whose decisions are not *near-ties* in the
+oracle's own float64 arithmetic; near-tie / degenerate columns are counted and reported, not
+hidden.  A column is excluded from the support comparison iff, at any executed greedy step,
+  * the oracle's relative top-1/top-2 gap of |alpha| is below GAP_TOL (float32 rounding of the
+    inputs alone can flip such an argmax), or
+  * the oracle's Cholesky pivot 1 - w.w is below PIVOT_TOL (near-duplicate atoms), or
+  * the oracle selected fewer than k atoms (it hit a break: degenerate column).
+Coefficients: max |Z_gpu - Z_ref| / max |Z_ref| <= COEF_TOL over the compared columns.
+"""
+import numpy as np
+
+GAP_TOL = 1e-5
+PIVOT_TOL = 1e-6
+COEF_TOL = 1e-5
+
+
+def sorted_codes(idx, val):
+    """order-free view of (idx,val)[N,k]: ascending atom index, -1 pads last."""
+    idx = np.asarray(idx).astype(np.int64)
+    val = np.asarray(val, dtype=np.float64)
+    key = np.where(idx < 0, np.iinfo(np.int64).max, idx)
+    order = np.argsort(key, axis=1, kind="stable")
+    return np.take_along_axis(idx, order, axis=1), np.take_along_axis(val, order, axis=1)
+
+
+def comparable_columns(gap, vs, nsel, k):
+    gap = np.asarray(gap); vs = np.asarray(vs); nsel = np.asarray(nsel)
+    ok = (np.min(gap, axis=1) >= GAP_TOL) & (np.min(vs, axis=1) >= PIVOT_TOL) & (nsel == k)
+    return ok
+
+
+def check_codes(idx_gpu, val_gpu, idx_ref, val_ref, ok=None, coef_tol=COEF_TOL, label=""):
+    """Assert identical supports and close coefficients on the comparable columns.
+    Returns a small report dict."""
+    ig, vg = sorted_codes(idx_gpu, val_gpu)
+    ir, vr = sorted_codes(idx_ref, val_ref)
+    N = ig.shape[0]
+    if ok is None:
+        ok = np.ones(N, dtype=bool)
+    same = np.all(ig == ir, axis=1)
+    bad = np.flatnonzero(ok & ~same)
+    assert bad.size == 0, "%s: %d of %d comparable columns have a different support (first: col %d gpu=%s ref=%s)" % (
+        label, bad.size, int(ok.sum()), bad[0], ig[bad[0]], ir[bad[0]])
+    both = ok & same
+    scale = np.max(np.abs(vr[both])) if both.any() else 1.0
+    err = np.max(np.abs(vg[both] - vr[both])) / scale if both.any() else 0.0
+    assert err <= coef_tol, "%s: coefficient rel-inf error %.3g > %.3g" % (label, err, coef_tol)
+    return {"columns": int(N), "compared": int(both.sum()), "excluded": int((~ok).sum()),
+            "mismatch_in_excluded": int((~ok & ~same).sum()), "coef_rel_inf": float(err)}

@@ -1,0 +1,53 @@
+"""CPU: the C-ABI library builds, loads, and exports exactly what include/lyssa_b200.h
+declares; the Python binding table covers every declaration.  No compute calls here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from lyssandra_b200 import _native, _build
+
+HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "lyssa_b200.h")
+
+
+def _declared():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lys_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _native.load()
+    names = _declared()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), "liblyssa_b200.so lacks %s declared in include/lyssa_b200.h" % name
+    assert sorted(_native.SIGNATURES) == names, "binding table and header disagree"
+
+
+def test_library_is_in_tree_and_sm100a():
+    path = _native.lib_path()
+    assert os.path.isfile(path) and path.startswith(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert "compute_100a" in " ".join(_build.NVCC_FLAGS)
+
+
+def test_pure_host_entry_points():
+    lib = _native.load()
+    assert lib.lys_version() >= 100
+    # workspace queries are host arithmetic only
+    assert lib.lys_bomp_workspace_bytes(64, 1024, 1 << 20, 5) >= 1024 * 1024 * 4
+    assert lib.lys_bomp_workspace_bytes(0, 1024, 10, 5) == 0
+    assert lib.lys_residual_workspace_bytes(64, 1024, 1000) >= 64 * 1024 * 4
+    assert lib.lys_ksvd_sweep_workspace_bytes(64, 1024) >= 64 * 1024 * 4
+    assert lib.lys_odl_update_workspace_bytes(128, 2048) >= 128 * 2048 * 4
+    # argument validation happens before any CUDA call
+    rc = lib.lys_bomp_encode(None, 1, 64, None, 1024, None, 64, 1024, 10, 0, None, None, None, None, 1, 1024, None, 0, None)
+    assert rc == _native.LYS_EINVAL
+    assert b"n_nonzero_coefs" in lib.lys_last_error()
+    rc = lib.lys_bomp_encode(None, 1, 64, None, 1024, None, 64, 5000, 10, 5, None, None, None, None, 1, 5000, None, 0, None)
+    assert rc == _native.LYS_EINVAL and b"K=5000" in lib.lys_last_error()
+    with pytest.raises(_native.LyssaError):
+        _native.check(rc)
+    out = ctypes.c_void_p()
+    assert lib.lys_comm_create(0, 1, ctypes.byref(out)) == 0

@@ -1,0 +1,106 @@
+"""CPU: host-side logic of the reference-facing layer — error behaviour pinned by the
+reference's own tests, column partitions, the near-tie policy helper, and the world_size-2
+(gloo) sharding arithmetic used by the multi-GPU paths."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from lyssandra_b200.sparse_coding import sparse_encoder
+from lyssandra_b200 import utils as lutils
+from oracle import lyssa_oracle as lo
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import parity  # noqa: E402
+
+
+def test_invalid_encoder_raises_like_the_reference():
+    # lyssa/tests/test_sparse_coding.py:10-19
+    X = np.random.rand(10, 100)
+    D = np.random.rand(10, 4)
+    se = sparse_encoder(algorithm="se", params={"n_nonzero_coefs": 4})
+    with pytest.raises(ValueError, match="Sparse optimizer not found"):
+        se.encode(X, D)
+
+
+def test_other_reference_coders_do_not_fall_back_to_cpu():
+    se = sparse_encoder(algorithm="omp", params={"n_nonzero_coefs": 4})
+    with pytest.raises(NotImplementedError):
+        se.encode(np.zeros((4, 3)), np.eye(4))
+    with pytest.raises(ValueError):
+        sparse_encoder(algorithm="bomp", params={}).encode(np.zeros((4, 3)), np.eye(4))
+
+
+def test_public_attributes_are_mutable_like_the_reference():
+    se = sparse_encoder(algorithm="bomp", params={"n_nonzero_coefs": 3}, n_jobs=2, verbose=True)
+    se.mmap = True; se.verbose = False; se.params["n_nonzero_coefs"] = 5; se.n_jobs = 1
+    assert (se.algorithm, se.name, se.mmap, se.verbose, se.n_jobs) == ("bomp", "sparse_coder", True, False, 1)
+    assert sparse_encoder().algorithm == "omp" and sparse_encoder().params == {}
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful without a GPU")
+def test_bomp_without_gpu_fails_loudly():
+    se = sparse_encoder(algorithm="bomp", params={"n_nonzero_coefs": 2})
+    with pytest.raises(RuntimeError, match="CUDA|no CPU path|status"):
+        se.encode(np.zeros((4, 3), dtype=np.float32), np.eye(4, dtype=np.float32))
+
+
+@pytest.mark.parametrize("N,nb", [(250, 100), (50, 100), (1000, 7)])
+def test_partitions_match_the_oracle(N, nb):
+    a = [(r.start, r.stop) for r in lutils.gen_even_batches(N, nb)]
+    b = [(r.start, r.stop) for r in lo.gen_even_batches(N, nb)]
+    assert a == b
+    assert [(r.start, r.stop) for r in lutils.gen_batches(N, 64)] == [(r.start, r.stop) for r in lo.gen_batches(N, 64)]
+    assert lutils.gen_batches(N) == [range(0, N)]
+
+
+def test_shard_bounds_cover_all_columns():
+    for N, W in ((1000, 8), (1001, 8), (7, 2), (1 << 20, 4)):
+        spans = [lutils.shard_bounds(N, W, r) for r in range(W)]
+        assert spans[0][0] == 0 and spans[-1][1] == N
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(W - 1))
+
+
+def test_parity_policy_helper():
+    idx_ref = np.array([[1, 4, 9], [2, 3, -1]]); val_ref = np.array([[1.0, -2.0, 0.5], [3.0, 1.0, 0.0]])
+    idx_gpu = np.array([[9, 1, 4], [3, 2, -1]]); val_gpu = np.array([[0.5, 1.0, -2.0], [1.0, 3.0, 0.0]])
+    rep = parity.check_codes(idx_gpu, val_gpu, idx_ref, val_ref)
+    assert rep["compared"] == 2 and rep["coef_rel_inf"] == 0.0
+    with pytest.raises(AssertionError):
+        parity.check_codes(np.array([[9, 1, 5]]), val_gpu[:1], idx_ref[:1], val_ref[:1])
+    ok = parity.comparable_columns(np.array([[1e-3, 1e-7], [1e-2, 1e-2]]), np.ones((2, 2)), np.array([2, 2]), 2)
+    assert list(ok) == [False, True]
+
+
+def _gloo_worker(rank, world, port, N, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lyssandra_b200 import distributed as ldist
+    ctx = ldist.DistContext.from_env_or_group()
+    lo_, hi_ = ctx.shard(N)
+    # sufficient statistics summed over ranks == statistics of the whole batch
+    rng = np.random.default_rng(0)
+    Z = torch.from_numpy(rng.standard_normal((6, N)))
+    X = torch.from_numpy(rng.standard_normal((4, N)))
+    A = Z[:, lo_:hi_] @ Z[:, lo_:hi_].T
+    B = X[:, lo_:hi_] @ Z[:, lo_:hi_].T
+    ctx.allreduce_sum_(A); ctx.allreduce_sum_(B)
+    cnt = torch.tensor([hi_ - lo_], dtype=torch.int64)
+    ctx.allreduce_sum_(cnt)
+    gathered = ctx.allgather_bytes(bytes([rank]) * 4)
+    ok = (torch.allclose(A, Z @ Z.T) and torch.allclose(B, X @ Z.T) and int(cnt) == N
+          and gathered == [bytes([r]) * 4 for r in range(world)])
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_sharding_and_suffstat_allreduce():
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_worker, args=(2, port, 1001, out), nprocs=2, join=True)
+    assert dict(out) == {0: True, 1: True}

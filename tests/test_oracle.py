@@ -1,0 +1,149 @@
+"""CPU: the oracle against (a) the committed golden vectors produced by the LIVE reference
+(oracle/gen_golden.py), (b) the live reference itself when /root/reference is present,
+(c) its own C restatement.  This is what pins the checker before it is trusted."""
+import numpy as np
+import pytest
+
+from oracle import lyssa_oracle as lo
+from oracle import c_oracle as co
+from oracle import ref_loader as rl
+
+
+def _dense_from_sorted(idx, val, K):
+    N, k = idx.shape
+    Z = np.zeros((K, N))
+    for i in range(N):
+        m = idx[i] >= 0
+        Z[idx[i][m], i] = val[i][m]
+    return Z
+
+
+def _bomp(X, D, k):
+    return lo.sparse_encoder("bomp", {"n_nonzero_coefs": k}, verbose=False).encode(X.astype(float), D.astype(float))
+
+
+@pytest.mark.parametrize("name,keys", [("bomp_cfg1", [("idx", "val", None)]),
+                                        ("bomp_cfg4", [("idx", "val", None)]),
+                                        ("bomp_K1024", [("idx_k5", "val_k5", 5), ("idx_k10", "val_k10", 10)])])
+def test_batch_omp_matches_golden(golden, name, keys):
+    g = golden(name)
+    for ik, vk, k in keys:
+        k = int(g["k"]) if k is None else k
+        Z = _bomp(g["X"], g["D"], k)
+        Zg = _dense_from_sorted(g[ik], g[vk], g["D"].shape[1])
+        assert np.array_equal(Z != 0, Zg != 0)
+        assert np.max(np.abs(Z - Zg)) <= 1e-13
+
+
+def test_kats_match_golden(golden):
+    g = golden("bomp_kat")
+    assert np.array_equal(_bomp(g["ortho_X"], g["ortho_D"], 3), g["ortho_Z"])
+    # orthonormal D: Z is the top-3 of alpha by magnitude
+    alpha = g["ortho_D"].astype(float).T @ g["ortho_X"].astype(float)
+    Z = g["ortho_Z"]
+    for i in range(alpha.shape[1]):
+        top = np.sort(np.argsort(-np.abs(alpha[:, i]), kind="stable")[:3])
+        assert np.array_equal(np.flatnonzero(Z[:, i]), top)
+        assert np.allclose(Z[top, i], alpha[top, i], atol=1e-6)
+    Zt = _bomp(g["ties_X"], g["ties_D"], 2)
+    assert np.array_equal(Zt, g["ties_Z"])
+    assert np.array_equal(np.flatnonzero(Zt[:, 0]), [0, 1])       # |3|,|-3|,|3| tie -> lowest indices
+    assert np.array_equal(np.flatnonzero(Zt[:, 2]), [0, 1])       # all ones -> 0 then 1
+    assert np.array_equal(_bomp(g["kK_X"], g["kK_D"], 4), g["kK_Z"])
+    assert np.array_equal(_bomp(g["k12_X"], g["k12_D"], 1), g["k1_Z"])
+    assert np.array_equal(_bomp(g["k12_X"], g["k12_D"], 2), g["k2_Z"])
+    assert np.array_equal(_bomp(g["degen_X"], g["k12_D"], 4), g["degen_Z"])
+    assert np.count_nonzero(g["degen_Z"][:, 1]) == 0            # zero signal: argmax 0, coefficient 0.0
+    assert np.array_equal(_bomp(g["k12_X"], g["dup_D"], 3), g["dup_Z"])
+    assert np.array_equal(lo.normalize(np.zeros(5)), g["norm_zero"])
+    assert np.allclose(lo.normalize(g["norm_vec_in"]), g["norm_vec_out"], rtol=0, atol=1e-16)
+    assert np.allclose(lo.norm_cols(g["norm_cols_in"].copy()), g["norm_cols_out"], rtol=0, atol=1e-16)
+
+
+def test_approx_ksvd_matches_golden(golden):
+    g = golden("ksvd_sweep")
+    X, D0, k = g["X"].astype(float), g["D"].astype(float), int(g["k"])
+    Z0 = _dense_from_sorted(g["Z_idx"], g["Z_val"], D0.shape[1])
+    N = X.shape[1]
+    for cyc in (1, 2):
+        D, Z = D0.copy(), Z0.copy()
+        _, _, unused = lo.approx_ksvd(X, D, Z, n_cycles=cyc)
+        assert np.max(np.abs(D - g["D_c%d" % cyc])) <= 1e-13
+        got = Z[np.maximum(g["Z_idx"], 0), np.arange(N)[:, None]] * (g["Z_idx"] >= 0)
+        assert np.max(np.abs(got - g["Zval_c%d" % cyc])) <= 1e-12
+        assert list(unused) == list(g["unused_c%d" % cyc])
+        assert abs(lo.approx_error(D, Z, X) - float(g["err_c%d" % cyc])) <= 1e-9 * float(g["err_c%d" % cyc])
+    assert len(g["unused_c1"]) > 0          # the fixture exercises the unused-atom branch
+
+
+def test_ksvd_learn_and_odl_match_golden(golden):
+    g = golden("ksvd_learn")
+    X = g["X"].astype(float)
+    for tag, init in (("arr", g["D0"].astype(float)), ("data", "data")):
+        np.random.seed(int(g["seed_%s" % tag]))
+        D, Z = lo.ksvd_dict_learn(X, 96, init_dict=init, sparse_coder=lo.sparse_encoder("bomp", {"n_nonzero_coefs": 4}),
+                                  max_iter=3, approx=True, verbose=False)
+        assert np.max(np.abs(D - g["D_%s" % tag])) <= 1e-12
+        assert abs(lo.approx_error(D, Z, X) - float(g["err_%s" % tag])) <= 1e-9 * float(g["err_%s" % tag])
+    g = golden("odl")
+    X = g["X"].astype(float)
+    for tag, beta, nn in (("lin", None, False), ("b09nn", 0.9, True)):
+        D, A, B = lo.online_dict_learn(X, 96, sparse_coder=lo.sparse_encoder("bomp", {"n_nonzero_coefs": 4}),
+                                       batch_size=128, D_init=g["D0"].astype(float).copy(), beta=beta, n_epochs=2, non_neg=nn)
+        assert np.max(np.abs(D - g["D_%s" % tag])) <= 1e-12
+        assert np.max(np.abs(A - g["A_%s" % tag])) <= 1e-12
+        assert np.max(np.abs(B - g["B_%s" % tag])) <= 1e-12
+
+
+def test_init_dictionary_matches_golden(golden):
+    g = golden("init_dict")
+    np.random.seed(int(g["seed"]))
+    D, unused = lo.init_dictionary(g["X"].astype(float), 12, method="data", return_unused_data=True)
+    assert np.max(np.abs(D - g["D"])) <= 1e-15
+    assert list(unused) == list(g["unused"])
+    assert 5 not in unused and 17 not in unused     # zero columns are not candidates
+
+
+def test_c_oracle_matches_numpy_oracle():
+    X = lo.synthetic_patches(600, 64, seed=12).astype(float)
+    D = lo.synthetic_dictionary(512, 64, seed=13).astype(float)
+    for k in (1, 2, 5, 10):
+        tr = {}
+        Z = lo.batch_omp(X, D.T @ X, D, D.T @ D, k, trace=tr)
+        idx, val, nsel, gap, vs = co.batch_omp_sparse(X, D, k, threads=2, trace=True)
+        Zc = co.densify(idx, val, 512)
+        assert np.array_equal(Z != 0, Zc != 0)
+        assert np.max(np.abs(Z - Zc)) <= 1e-13
+        assert np.array_equal(nsel, tr["nsel"])
+        assert np.allclose(gap, tr["gap"], rtol=1e-9, atol=1e-14)
+
+
+def test_batches_and_quirks():
+    assert [len(r) for r in lo.gen_even_batches(250, 100)] == [2] * 99 + [52]
+    assert [len(r) for r in lo.gen_even_batches(50, 100)] == [0] * 99 + [50]      # quirk Q8
+    assert [(r.start, r.stop) for r in lo.gen_batches(10, 4)] == [(0, 4), (4, 8), (8, 10)]
+    with pytest.raises(ValueError):
+        lo.sparse_encoder(algorithm="se", params={"n_nonzero_coefs": 4}).encode(np.zeros((4, 3)), np.eye(4))
+
+
+@pytest.mark.skipif(not rl.available(), reason="reference tree not present (GPU box)")
+def test_oracle_matches_live_reference():
+    ref = rl.load()
+    X = lo.synthetic_patches(300, 64, seed=20).astype(float)
+    D = lo.synthetic_dictionary(256, 64, seed=21).astype(float)
+    with rl.quiet():
+        Zr = ref.sparse_encoder("bomp", {"n_nonzero_coefs": 5}, verbose=False).encode(X, D)
+    Zo = _bomp(X, D, 5)
+    assert np.array_equal(Zr, Zo)
+    Dr, Zr2, Do, Zo2 = D.copy(), Zr.copy(), D.copy(), Zo.copy()
+    with rl.quiet():
+        _, _, ur = ref.approx_ksvd(X, Dr, Zr2, n_cycles=1, verbose=False)
+    _, _, uo = lo.approx_ksvd(X, Do, Zo2)
+    assert ur == uo and np.max(np.abs(Dr - Do)) <= 1e-14 and np.max(np.abs(Zr2 - Zo2)) <= 1e-13
+    np.random.seed(5)
+    with rl.quiet():
+        D1, A1, B1 = ref.online_dict_learn(X, 40, sparse_coder=ref.sparse_encoder("bomp", {"n_nonzero_coefs": 3}, verbose=False),
+                                           batch_size=64, n_epochs=2)
+    np.random.seed(5)
+    D2, A2, B2 = lo.online_dict_learn(X, 40, sparse_coder=lo.sparse_encoder("bomp", {"n_nonzero_coefs": 3}), batch_size=64, n_epochs=2)
+    assert np.max(np.abs(D1 - D2)) <= 1e-14 and np.max(np.abs(A1 - A2)) <= 1e-13 and np.max(np.abs(B1 - B2)) <= 1e-13
