@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the Batch-OMP encode path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): Batch-OMP encode of 1 M synthetic 8x8 grayscale patches
+(uniform pixels, mean removed), D 64x1024 unit-norm, k = 5, fp32, dense Z (K x N) written —
+per GPU (weak scaling: every rank encodes its own 1 M patches, no data-path collective).
+A "step" is one full encode of that batch: Gram + correlations + greedy + dense-Z write.
+
+Own arm: inputs resident in HBM, CUDA events on the launching stream, barrier + synchronize on
+both sides, max over ranks.  `e2e` times the same step through the host-buffer C-ABI call
+(lys_bomp_encode_host) with pinned host X in and pinned dense Z out, copies inside the timed
+region.  `roofline` is measured live: CUDA events around every launch of the dominant kernel
+(lys_profile_*), algorithmic bytes = (4n + 4K) per patch.  `cpu_baseline` is the
+NumPy oracle (bit-identical restatement of the reference) run the reference's way
+(sparse_encoder('bomp', n_jobs=cores): process pool over 100 column batches, 1 BLAS thread per
+worker) on a bounded contiguous sample, rank 0 at N=1 only, in a subprocess.
+
+Reference arm (--impl reference): that same CPU path, all host cores, one bounded sample per
+step; under torchrun only rank 0 works.  It never touches CUDA.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_PER_GPU = 1 << 20
+N_FEATURES, N_ATOMS, K_NONZERO = 64, 1024, 5
+METRIC, UNIT = "batch_omp_patches_per_sec", "patches/s"
+WORKLOAD = "Batch-OMP encode, 1M synthetic 8x8 grayscale patches per GPU, D 64x1024, k=5, fp32, dense Z written"
+
+
+def config(n_gpus):
+    return {"workload": WORKLOAD, "n_features": N_FEATURES, "n_atoms": N_ATOMS, "n_nonzero_coefs": K_NONZERO,
+            "patches_per_gpu": N_PER_GPU, "global_patches": N_PER_GPU * n_gpus,
+            "parallelism": "patch-sharded x%d, no collective" % n_gpus,
+            "l2_policy": "inputs larger than L2 (X 256 MiB, Z 4 GiB per GPU per step; L2 126 MB)"}
+
+
+# ------------------------------------------------------------------------- reference arm
+def cpu_encode_rate(sample, cores, repeats=1):
+    """patches/s of the oracle's reference-regime encoder on `sample` columns."""
+    from oracle import lyssa_oracle as lo
+    X = lo.synthetic_patches(sample, N_FEATURES, seed=0).astype(np.float64)
+    D = lo.synthetic_dictionary(N_ATOMS, N_FEATURES, seed=1).astype(np.float64)
+    enc = lo.sparse_encoder("bomp", {"n_nonzero_coefs": K_NONZERO}, n_jobs=cores, verbose=False)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        Z = enc.encode(X, D)
+        best = min(best, time.perf_counter() - t0)
+    assert Z.shape == (N_ATOMS, sample)
+    return sample / best, best
+
+
+def pick_sample(cores, target_s):
+    """Calibrate on 1024 columns in-process (1 core), size the sample for ~target_s seconds."""
+    from oracle import lyssa_oracle as lo
+    X = lo.synthetic_patches(1024, N_FEATURES, seed=0).astype(np.float64)
+    D = lo.synthetic_dictionary(N_ATOMS, N_FEATURES, seed=1).astype(np.float64)
+    t0 = time.perf_counter()
+    lo.sparse_encoder("bomp", {"n_nonzero_coefs": K_NONZERO}, n_jobs=1, verbose=False).encode(X, D)
+    rate1 = 1024 / (time.perf_counter() - t0)
+    est = rate1 * max(1.0, 0.6 * cores)
+    sample = int(est * target_s)
+    step = 100 * max(cores, 1)
+    return max(step, min(262144, sample // step * step))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    sample = args.sample or pick_sample(cores, 5.0)
+    for _ in range(args.warmup if args.sample is None else 0):
+        cpu_encode_rate(min(sample, 100 * cores * 4), cores)
+    times = []
+    for _ in range(args.steps):
+        _, dt = cpu_encode_rate(sample, cores)
+        times.append(dt)
+    total = sum(times)
+    value = sample * len(times) / total
+    desc = ("first %d of the 1M patches per step (contiguous prefix), oracle = NumPy restatement pinned "
+            "bit-exact to the reference, run as sparse_encoder('bomp', n_jobs=%d)" % (sample, cores))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                mhz, mx = float(parts[1]), float(parts[2])
+            except ValueError:
+                continue
+            smax.append(mx)
+            if t0 <= t <= t1:
+                sm.append(mhz)
+                for name, flag in zip(names, parts[5:9]):
+                    if flag.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:
+            sm = [float(p.split(",")[1]) for _, p in self.rows[-3:] if len(p.split(",")) > 2] or [0.0]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax) if smax else 0.0,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- own arm
+def run_own(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+
+    # CPU baseline first, in a subprocess (a fork()ing process pool must not share a CUDA context)
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
+                                  "--warmup", "0", "--sample", str(pick_sample(os.cpu_count() or 1, 12.0))],
+                                 capture_output=True, text=True, timeout=600, cwd=ROOT)
+            cpu_base = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception as exc:  # reported, never silently dropped
+            cpu_base = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (exc,)}
+
+    import torch
+    import torch.distributed as dist
+    from lyssandra_b200 import _native, engine
+    from lyssandra_b200.sparse_coding import sparse_encoder
+    from oracle import lyssa_oracle as lo      # synthetic data generators only (bench input, not a checker call)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _native.load()
+    _native.check(lib.lys_device_info(local, None, None, None))
+
+    n, K, k, N = N_FEATURES, N_ATOMS, K_NONZERO, N_PER_GPU
+    Xh_sm = np.ascontiguousarray(lo.synthetic_patches(N, n, seed=rank).T)          # (N, n) signal-major storage
+    Dh = lo.synthetic_dictionary(K, n, seed=1)
+    X = torch.from_numpy(Xh_sm).to(dev).t()                                        # logical (n, N), resident in HBM
+    D = torch.from_numpy(Dh).to(dev)
+    enc = sparse_encoder("bomp", {"n_nonzero_coefs": k}, verbose=False)
+    idx = torch.empty((N, k), dtype=torch.int32, device=dev)
+    val = torch.empty((N, k), dtype=torch.float32, device=dev)
+    nsel = torch.empty((N,), dtype=torch.int32, device=dev)
+    Zt = torch.empty((N, K), dtype=torch.float32, device=dev)
+    G = torch.empty((K, K), dtype=torch.float32, device=dev)
+    wsb = lib.lys_bomp_workspace_bytes(n, K, N, k)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def step():
+        _native.check(lib.lys_gram(D.data_ptr(), K, n, K, G.data_ptr(), stream))
+        _native.check(lib.lys_bomp_encode(X.data_ptr(), X.stride(0), X.stride(1), D.data_ptr(), K, G.data_ptr(),
+                                          n, K, N, k, idx.data_ptr(), val.data_ptr(), nsel.data_ptr(),
+                                          Zt.data_ptr(), 1, K, ws.data_ptr(), wsb, stream))
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    lib.lys_profile_fetch(None, None, None, 1)
+    lib.lys_profile_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    t_begin = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    sync_all()
+    t_end = time.perf_counter()
+    lib.lys_profile_enable(0)
+    ms = e0.elapsed_time(e1)
+    kms, kl, kname = ctypes.c_double(), ctypes.c_int64(), ctypes.c_char_p()
+    _native.check(lib.lys_profile_fetch(ctypes.byref(kms), ctypes.byref(kl), ctypes.byref(kname), 1))
+    # second timed region under load for the clocks record if the first was too short to sample
+    if t_end - t_begin < 0.5:
+        t_begin2 = time.perf_counter()
+        while time.perf_counter() - t_begin2 < 0.6:
+            step()
+        torch.cuda.synchronize(dev)
+        t_begin, t_end = t_begin2, time.perf_counter()
+    sampler.stop()
+    clocks = sampler.summary(t_begin, t_end)
+
+    # sanity on the result the timed steps produced (cheap, after timing)
+    assert int(nsel.min()) == k and int((idx < 0).sum()) == 0
+    assert int((Zt[:4096] != 0).sum()) == 4096 * k
+
+    # ---- e2e: host buffers through the C-ABI, copies inside the timed region
+    Xpin = torch.from_numpy(Xh_sm).pin_memory()
+    Zpin = torch.empty((N, K), dtype=torch.float32).pin_memory()
+    Dpin = torch.from_numpy(Dh).pin_memory()
+
+    def e2e_step():
+        _native.check(lib.lys_bomp_encode_host(Xpin.data_ptr(), 1, n, Dpin.data_ptr(), K, n, K, N, k,
+                                               None, None, None, Zpin.data_ptr(), 1, K, local))
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    assert int((Zpin[:4096] != 0).sum()) == 4096 * k
+    # sparse-output variant (what the learners consume): no dense Z over PCIe
+    ipin = torch.empty((N, k), dtype=torch.int32).pin_memory()
+    vpin = torch.empty((N, k), dtype=torch.float32).pin_memory()
+    spin = torch.empty((N,), dtype=torch.int32).pin_memory()
+    _native.check(lib.lys_bomp_encode_host(Xpin.data_ptr(), 1, n, Dpin.data_ptr(), K, n, K, N, k,
+                                           ipin.data_ptr(), vpin.data_ptr(), spin.data_ptr(), None, 1, K, local))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        _native.check(lib.lys_bomp_encode_host(Xpin.data_ptr(), 1, n, Dpin.data_ptr(), K, n, K, N, k,
+                                               ipin.data_ptr(), vpin.data_ptr(), spin.data_ptr(), None, 1, K, local))
+    e2e_sparse_s = time.perf_counter() - t0
+
+    t = torch.tensor([ms, e2e_s * 1e3 / e2e_steps, e2e_sparse_s * 1e3 / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms, e2e_sparse_ms = [float(v) for v in t.tolist()]
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        bytes_per_patch = 4 * n + 4 * K
+        launches_k = int(kl.value)
+        achieved = (bytes_per_patch * N * args.steps / 1e9) / (kms.value / 1e3) if kms.value > 0 else 0.0
+        total_patches = N * world * args.steps
+        line = {
+            "metric": METRIC, "value": total_patches / (ms_max / 1e3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config(world),
+            "clocks": clocks,
+            "e2e": {"value": N * world / (e2e_ms / 1e3), "unit": UNIT,
+                    "h2d_bytes_per_step": (N * n * 4 + n * K * 4) * world, "d2h_bytes_per_step": N * K * 4 * world,
+                    "api": "lys_bomp_encode_host: pinned host X -> pinned host dense Z (what sparse_encoder.encode(numpy) calls)",
+                    "sparse_output_variant": {"value": N * world / (e2e_sparse_ms / 1e3), "unit": UNIT,
+                                              "d2h_bytes_per_step": N * (8 * k + 4) * world,
+                                              "note": "same call returning (idx,val,nsel) instead of dense Z"}},
+            "gpu_launches": (lib.lys_bomp_launch_count(n, K, N, k) + 1) * args.steps,
+            "roofline": {"bound": "hbm", "kernel": (kname.value or b"").decode(), "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
+                         "launches_timed": launches_k, "kernel_ms_per_step": kms.value / args.steps,
+                         "kernel_share_of_step": kms.value / ms if ms > 0 else None,
+                         "algorithmic_bytes_per_patch": bytes_per_patch, "peak_source": peak_src,
+                         "step_level": {"achieved": bytes_per_patch * N * args.steps / 1e9 / (ms / 1e3),
+                                        "frac": bytes_per_patch * N * args.steps / 1e9 / (ms / 1e3) / peak}},
+            "cpu_baseline": cpu_base,
+        }
+        traffic_file = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
+        if os.path.isfile(traffic_file):
+            try:
+                line["roofline"]["traffic"] = json.load(open(traffic_file)).get(line["roofline"]["kernel"])
+            except Exception:
+                pass
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--sample", type=int, default=None, help="(reference arm) columns per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_own(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -55,6 +55,16 @@ LYS_API const char* lys_last_error(void);
 /* SM count / compute capability of `device`; fails unless it is an sm_100 part. */
 LYS_API int         lys_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
 
+/* ---- measurement hooks (bench.py) ------------------------------------------------------
+ * lys_bomp_launch_count: number of kernel launches ONE lys_bomp_encode call with these
+ * shapes performs (bench.py's gpu_launches claim).
+ * lys_profile_enable(1): every launch of the encode path's DOMINANT kernel is bracketed by
+ * CUDA events on its own stream; lys_profile_fetch synchronises those events and returns
+ * the summed device time (ms), the number of launches and the kernel's name. */
+LYS_API int lys_bomp_launch_count(int n, int K, int64_t N, int k);
+LYS_API int lys_profile_enable(int on);
+LYS_API int lys_profile_fetch(double* kernel_ms, int64_t* launches, const char** kernel_name, int reset);
+
 /* ---- K1: Gram = D^T D --------------------------------------------------------------
  * replaces `Gram = fast_dot(D.T, D)`, lyssa/sparse_coding.py:630.  G is (K,K) row-major. */
 LYS_API int lys_gram(const float* D, int64_t ldd, int n, int K, float* G, void* stream);

@@ -19,6 +19,9 @@ SIGNATURES = {
     "lys_version": (c_int, []),
     "lys_last_error": (ctypes.c_char_p, []),
     "lys_device_info": (c_int, [c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    "lys_bomp_launch_count": (c_int, [c_int, c_int, c_i64, c_int]),
+    "lys_profile_enable": (c_int, [c_int]),
+    "lys_profile_fetch": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_i64), ctypes.POINTER(ctypes.c_char_p), c_int]),
     "lys_gram": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
     "lys_bomp_workspace_bytes": (c_sz, [c_int, c_int, c_i64, c_int]),
     "lys_bomp_encode": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_i64, c_int,

@@ -19,6 +19,32 @@ int bomp_encode_fused(const float* X, int64_t xfs, int64_t xss, const float* D, 
                       float* Z, int64_t zas, int64_t zss,
                       void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t bomp_fused_workspace_bytes(int n, int K, int64_t N, int k);
+int bomp_fused_launch_count(int n, int K, int64_t N, int k);
+
+// ---- dominant-kernel profiling (see lys_profile_enable in the header)
+struct ProfState {
+    bool on = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> used, pool;
+    const char* name = "none";
+};
+static ProfState g_prof;
+static std::mutex g_prof_mu;
+
+bool profile_begin(cudaStream_t st, const char* name, cudaEvent_t* stop_out)
+{
+    if (!g_prof.on) return false;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    if (!g_prof.pool.empty()) { ev = g_prof.pool.back(); g_prof.pool.pop_back(); }
+    else {
+        if (cudaEventCreate(&ev.first) != cudaSuccess || cudaEventCreate(&ev.second) != cudaSuccess) return false;
+    }
+    cudaEventRecord(ev.first, st);
+    g_prof.used.push_back(ev);
+    g_prof.name = name;
+    *stop_out = ev.second;
+    return true;
+}
 
 namespace {
 
@@ -106,10 +132,49 @@ extern "C" int lys_bomp_encode(const float* X, int64_t xfs, int64_t xss,
         const int64_t C = std::min(chunk, N - s0);
         rc = sgemm_strided(X + s0 * xss, xss, xfs, D, ldd, 1, alpha, K, 1, C, K, n, stream);
         if (rc) return rc;
+        cudaEvent_t stop_ev;
+        const bool prof = profile_begin(stream, "bomp_warp_kernel", &stop_ev);
         rc = bomp_greedy_generic(alpha, G, K, C, k, idx + s0 * k, val + s0 * k,
                                  nsel ? nsel + s0 : nullptr,
                                  Z ? Z + s0 * zss : nullptr, zas, zss, stream);
+        if (prof) cudaEventRecord(stop_ev, stream);
         if (rc) return rc;
+    }
+    return LYS_OK;
+}
+
+extern "C" int lys_bomp_launch_count(int n, int K, int64_t N, int k)
+{
+    if (n < 1 || K < 1 || N < 1 || k < 1) return 0;
+    int fused = bomp_fused_launch_count(n, K, N, k);
+    if (fused > 0) return fused;
+    const int64_t chunk = generic_chunk(K, N);
+    return (int)(2 * ((N + chunk - 1) / chunk));
+}
+
+extern "C" int lys_profile_enable(int on)
+{
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.on = on != 0;
+    return LYS_OK;
+}
+
+extern "C" int lys_profile_fetch(double* kernel_ms, int64_t* launches, const char** kernel_name, int reset)
+{
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    double total = 0.0;
+    for (auto& ev : g_prof.used) {
+        LYS_CUDA(cudaEventSynchronize(ev.second));
+        float ms = 0.f;
+        LYS_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+        total += ms;
+    }
+    if (kernel_ms) *kernel_ms = total;
+    if (launches) *launches = (int64_t)g_prof.used.size();
+    if (kernel_name) *kernel_name = g_prof.name;
+    if (reset) {
+        for (auto& ev : g_prof.used) g_prof.pool.push_back(ev);
+        g_prof.used.clear();
     }
     return LYS_OK;
 }

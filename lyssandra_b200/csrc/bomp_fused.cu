@@ -6,6 +6,7 @@
 namespace lys {
 
 size_t bomp_fused_workspace_bytes(int, int, int64_t, int) { return 0; }
+int bomp_fused_launch_count(int, int, int64_t, int) { return 0; }
 
 int bomp_encode_fused(const float*, int64_t, int64_t, const float*, int64_t, const float*,
                       int, int, int64_t, int, int32_t*, float*, int32_t*, float*, int64_t, int64_t,

@@ -1,0 +1,206 @@
+"""GPU parity tests of the dictionary-update half: residual/error, users-of-atom CSR, the
+approximate K-SVD sweep, the K-SVD outer loop, and the ODL update — against the golden
+vectors written by the live reference and against the oracle on seeded inputs."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from oracle import lyssa_oracle as lo  # noqa: E402
+from lyssandra_b200 import engine  # noqa: E402
+from lyssandra_b200.sparse_coding import sparse_encoder  # noqa: E402
+from lyssandra_b200.dict_learning import (approx_ksvd, ksvd_dict_learn, ksvd_coder, online_dict_learn,  # noqa: E402
+                                          online_dictionary_coder, dictionary_learner, init_dictionary, approx_error)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _enc(k):
+    return sparse_encoder(algorithm="bomp", params={"n_nonzero_coefs": k}, verbose=False)
+
+
+def _codes(idx, val, K):
+    idx_t = torch.from_numpy(np.ascontiguousarray(idx.astype(np.int32))).to(DEV)
+    val_t = torch.from_numpy(np.ascontiguousarray(val.astype(np.float32))).to(DEV)
+    return engine.SparseCodes(idx_t, val_t, (idx_t >= 0).sum(dim=1).to(torch.int32), K)
+
+
+def _dense(idx, val, K):
+    N, k = idx.shape
+    Z = np.zeros((K, N))
+    for i in range(N):
+        m = idx[i] >= 0
+        Z[idx[i][m], i] = val[i][m]
+    return Z
+
+
+def test_residual_error_and_csr(golden):
+    g = golden("ksvd_sweep")
+    X = torch.from_numpy(g["X"]).to(DEV); D = torch.from_numpy(g["D"]).to(DEV)
+    K = g["D"].shape[1]
+    codes = _codes(g["Z_idx"], g["Z_val"], K)
+    R, err = engine.residual(X, D, codes)
+    Zd = _dense(g["Z_idx"], g["Z_val"], K)
+    Rref = g["X"].astype(float) - g["D"].astype(float) @ Zd
+    assert np.max(np.abs(R.cpu().numpy().T - Rref)) < 2e-6
+    assert abs(float(err.item()) - np.sum(Rref ** 2)) <= 1e-6 * np.sum(Rref ** 2)
+    assert abs(approx_error(D, codes, X) - lo.approx_error(g["D"].astype(float), Zd, g["X"].astype(float))) <= 1e-6 * np.sum(Rref ** 2)
+    # feature-major and signal-major X give the same residual
+    Xs = X.t().contiguous().t()
+    R2, err2 = engine.residual(Xs, D, codes)
+    assert torch.equal(R, R2) and float(err.item()) == float(err2.item())
+    rowptr, entries = engine.build_atom_csr(codes)
+    rp = rowptr.cpu().numpy(); en = entries.cpu().numpy()
+    flat = g["Z_idx"].reshape(-1); vals = g["Z_val"].reshape(-1)
+    for c in range(K):
+        want = np.flatnonzero((flat == c) & (vals != 0))
+        assert np.array_equal(en[rp[c]:rp[c + 1]], want)          # ascending, deterministic
+    assert rp[-1] == np.count_nonzero((flat >= 0) & (vals != 0))
+
+
+@pytest.mark.parametrize("cyc", [1, 2])
+def test_sweep_matches_golden(golden, cyc):
+    g = golden("ksvd_sweep")
+    K = g["D"].shape[1]
+    X = torch.from_numpy(g["X"]).to(DEV); D = torch.from_numpy(g["D"]).to(DEV).clone()
+    codes = _codes(g["Z_idx"], g["Z_val"], K)
+    D2, codes2, unused = approx_ksvd(X, D, codes, n_cycles=cyc, verbose=False)
+    assert D2 is D and codes2 is codes                               # in-place contract (ksvd.py:118-123,126)
+    assert sorted(set(unused)) == sorted(set(g["unused_c%d" % cyc].tolist()))
+    Dref = g["D_c%d" % cyc]
+    assert np.max(np.abs(D.cpu().numpy() - Dref)) <= 1e-4 * np.max(np.abs(Dref))
+    vref = g["Zval_c%d" % cyc]
+    assert np.max(np.abs(codes.val.cpu().numpy() - vref)) <= 1e-4 * np.max(np.abs(vref))
+    err = approx_error(D, codes, X)
+    assert abs(err - float(g["err_c%d" % cyc])) <= 1e-4 * float(g["err_c%d" % cyc])
+    # the support never changes; atoms stay unit norm
+    assert torch.equal(codes.idx.cpu(), torch.from_numpy(g["Z_idx"].astype(np.int32)))
+    used = np.setdiff1d(np.arange(K), g["unused_c%d" % cyc])
+    assert np.max(np.abs(np.linalg.norm(D.cpu().numpy()[:, used], axis=0) - 1)) < 1e-5
+
+
+def test_sweep_vs_oracle_larger_and_monotone():
+    n, K, N, k = 64, 256, 6000, 6
+    Xh = lo.synthetic_patches(N, n, seed=31); Dh = lo.synthetic_dictionary(K, n, seed=32)
+    X = torch.from_numpy(np.ascontiguousarray(Xh)).to(DEV); D = torch.from_numpy(Dh).to(DEV).clone()
+    codes = _enc(k).encode_sparse(X, D)
+    idx = codes.idx.cpu().numpy(); val = codes.val.cpu().numpy().astype(np.float64)
+    Zd = _dense(idx, val, K)
+    Do = Dh.astype(np.float64).copy()
+    e0 = approx_error(D, codes, X)
+    lo.approx_ksvd(Xh.astype(np.float64), Do, Zd)
+    approx_ksvd(X, D, codes)
+    e1 = approx_error(D, codes, X)
+    assert e1 <= e0 * (1 + 1e-6)                                        # the sweep never increases the error
+    assert np.max(np.abs(D.cpu().numpy() - Do)) <= 1e-4
+    vo = Zd[np.maximum(idx, 0), np.arange(N)[:, None]] * (idx >= 0)
+    assert np.max(np.abs(codes.val.cpu().numpy() - vo)) <= 1e-4 * np.max(np.abs(vo))
+    assert abs(e1 - lo.approx_error(Do, Zd, Xh.astype(np.float64))) <= 1e-4 * e1
+
+
+def test_ksvd_dict_learn_matches_golden(golden):
+    g = golden("ksvd_learn")
+    X = torch.from_numpy(g["X"]).to(DEV)
+    for tag, init in (("arr", torch.from_numpy(g["D0"]).to(DEV)), ("data", "data")):
+        np.random.seed(int(g["seed_%s" % tag]))
+        hist = []
+        D, Z = ksvd_dict_learn(X, 96, init_dict=init, sparse_coder=_enc(4), max_iter=3, approx=True,
+                               n_cycles=1, verbose=False, history=hist)
+        assert tuple(D.shape) == (64, 96) and tuple(Z.shape) == (96, 400) and len(hist) == 3
+        # objective trajectory parity (D itself is chaotic once any support flips)
+        err = approx_error(D, Z, X)
+        assert abs(err - float(g["err_%s" % tag])) <= 1e-3 * float(g["err_%s" % tag])
+        assert abs(hist[-1]["error"] - err) <= 1e-5 * err
+        if tag == "arr":
+            assert np.max(np.abs(D.cpu().numpy() - g["D_arr"])) <= 5e-3
+            assert init.data_ptr() != D.data_ptr() and torch.equal(init.cpu(), torch.from_numpy(g["D0"]))   # :155 copy
+
+
+def test_ksvd_coder_quirk_q3_and_numpy_io():
+    Xh = np.ascontiguousarray(lo.synthetic_patches(1500, 64, seed=41))
+    np.random.seed(0)
+    coder = ksvd_coder(n_atoms=128, sparse_coder=_enc(3), init_dict="data", max_iter=20, approx=True, verbose=False)
+    coder.fit(Xh)
+    assert isinstance(coder.D, np.ndarray) and coder.D.shape == (64, 128)
+    assert len(coder.history) == 11                                    # quirk Q3: patience caps at 11 iterations
+    errs = [h["error"] for h in coder.history]
+    assert errs[-1] < errs[0]
+    Z = coder.encode(Xh)
+    assert isinstance(Z, np.ndarray) and Z.shape == (128, 1500) and np.all((Z != 0).sum(0) <= 3)
+    with pytest.raises(NotImplementedError):
+        ksvd_dict_learn(torch.zeros((64, 10), device=DEV), 8, sparse_coder=_enc(2), approx=False)
+
+
+def test_init_dictionary_matches_golden(golden):
+    g = golden("init_dict")
+    np.random.seed(int(g["seed"]))
+    D, unused = init_dictionary(torch.from_numpy(g["X"]).to(DEV), 12, method="data", return_unused_data=True)
+    assert np.max(np.abs(D.cpu().numpy() - g["D"])) <= 1e-6
+    assert list(unused) == list(g["unused"])
+    # the reference's own test: un-normalised atoms are data columns (dict_learning/tests/test_utils.py:15-27)
+    Xs = np.array([[1, 2, 3, 4, 5], [0, 2, 1, 2, 1]], dtype=np.float32)
+    Dn = init_dictionary(torch.from_numpy(Xs).to(DEV), 3, method="data", normalize=False).cpu().numpy()
+    assert Dn.shape == (2, 3)
+    assert sum(np.array_equal(Dn[:, i], Xs[:, j]) for i in range(3) for j in range(5)) == 3
+
+
+def test_odl_matches_golden(golden):
+    g = golden("odl")
+    X = torch.from_numpy(g["X"]).to(DEV)
+    for tag, beta, nn in (("lin", None, False), ("b09nn", 0.9, True)):
+        D0 = torch.from_numpy(g["D0"]).to(DEV).clone()
+        D, A, B = online_dict_learn(X, 96, sparse_coder=_enc(4), batch_size=128, D_init=D0, beta=beta,
+                                    n_epochs=2, non_neg=nn)
+        assert D.data_ptr() == D0.data_ptr()                            # D_init used without copying (:47)
+        assert np.max(np.abs(A.cpu().numpy() - g["A_%s" % tag])) <= 1e-3 * np.max(np.abs(g["A_%s" % tag]))
+        assert np.max(np.abs(B.cpu().numpy() - g["B_%s" % tag])) <= 1e-3 * np.max(np.abs(g["B_%s" % tag]))
+        assert np.max(np.abs(D.cpu().numpy() - g["D_%s" % tag])) <= 2e-3
+        if nn:
+            assert float(D.min()) >= 0.0
+
+
+def test_odl_single_step_vs_oracle():
+    """One minibatch from identical (D, A, B): isolates K12/K13 from encode flips."""
+    n, K, b, k = 128, 512, 1024, 5
+    Xh = np.ascontiguousarray(lo.synthetic_descriptors(b, n, seed=51))
+    rng = np.random.default_rng(52)
+    Dh = np.ascontiguousarray(lo.norm_cols(np.abs(rng.standard_normal((n, K)))).astype(np.float32))
+    X = torch.from_numpy(Xh).to(DEV); D = torch.from_numpy(Dh).to(DEV).clone()
+    codes = _enc(k).encode_sparse(X, D)
+    Zd = _dense(codes.idx.cpu().numpy(), codes.val.cpu().numpy().astype(np.float64), K)
+    A0 = rng.standard_normal((K, K)); A0 = (A0 @ A0.T / K).astype(np.float32); B0 = rng.standard_normal((n, K)).astype(np.float32)
+    A = torch.from_numpy(A0).to(DEV).clone(); B = torch.from_numpy(B0).to(DEV).clone()
+    engine.odl_accumulate_(X, codes, 0.7, A, B)
+    Ao = 0.7 * A0.astype(np.float64) + Zd @ Zd.T
+    Bo = 0.7 * B0.astype(np.float64) + Xh.astype(np.float64) @ Zd.T
+    assert np.max(np.abs(A.cpu().numpy() - Ao)) <= 1e-5 * np.max(np.abs(Ao))
+    assert np.max(np.abs(B.cpu().numpy() - Bo)) <= 1e-5 * np.max(np.abs(Bo))
+    for nn in (False, True):
+        Dg = torch.from_numpy(Dh).to(DEV).clone()
+        engine.odl_update_dict_(Dg, A, B, non_neg=nn)
+        Do = Dh.astype(np.float64).copy()
+        Af = A.cpu().numpy().astype(np.float64); Bf = B.cpu().numpy().astype(np.float64)
+        DA = Do @ Af
+        for c in range(K):
+            Do[:, c] = (1 / (Af[c, c] + lo.F64_EPS)) * (Bf[:, c] - DA[:, c]) + Do[:, c]
+        if nn:
+            Do[Do < 0] = 0
+        Do = lo.norm_cols(Do)
+        assert np.max(np.abs(Dg.cpu().numpy() - Do)) <= 2e-5
+
+
+def test_online_coder_and_gd_learner_shapes():
+    # the reference's only Batch-OMP-touching test (dict_learning/tests/test_dictionary_learn.py:11-21)
+    X = np.random.rand(10, 100).astype(np.float32)
+    np.random.seed(1)
+    dl = dictionary_learner(n_atoms=4, sparse_coder=_enc(4), eta=0.1, batch_size=None)
+    Z = dl(X)
+    assert Z.shape == (4, 100) and dl.D.shape == (10, 4)
+    np.random.seed(2)
+    oc = online_dictionary_coder(n_atoms=8, sparse_coder=_enc(2), batch_size=25, n_epochs=2)
+    Z = oc(X)
+    assert Z.shape == (8, 100) and oc.D.shape == (10, 8) and oc.A.shape == (8, 8) and oc.B.shape == (10, 8)
