@@ -5,12 +5,17 @@
 #include <mutex>
 #include <vector>
 #include <algorithm>
+#include <cstdlib>
 
 namespace lys {
 
 int bomp_greedy_generic(const float* alpha, const float* G, int K, int64_t C, int k,
                         int32_t* idx, float* val, int32_t* nsel,
                         float* Z, int64_t zas, int64_t zss, cudaStream_t stream);
+
+bool bomp_fast_supported(int K, int k, int64_t zas, bool has_Z, const float* Z, int64_t zss);
+int bomp_greedy_fast(const float* alpha, const float* G, int K, int64_t C, int k,
+                     int32_t* idx, float* val, int32_t* nsel, float* Z, int64_t zss, cudaStream_t stream);
 
 // fused tcgen05 path (bomp_fused.cu); returns LYS_EUNSUPPORTED for shapes it is not built for
 int bomp_encode_fused(const float* X, int64_t xfs, int64_t xss, const float* D, int64_t ldd,
@@ -128,15 +133,20 @@ extern "C" int lys_bomp_encode(const float* X, int64_t xfs, int64_t xss,
     // generic path: per chunk, Alpha = X_chunk^T D (fp32 GEMM) then one warp per signal
     float* alpha = reinterpret_cast<float*>(workspace);
     const int64_t chunk = generic_chunk(K, N);
+    const bool fast = bomp_fast_supported(K, k, zas, Z != nullptr, Z, zss) && !getenv("LYS_FORCE_GENERIC");
     for (int64_t s0 = 0; s0 < N; s0 += chunk) {
         const int64_t C = std::min(chunk, N - s0);
         rc = sgemm_strided(X + s0 * xss, xss, xfs, D, ldd, 1, alpha, K, 1, C, K, n, stream);
         if (rc) return rc;
         cudaEvent_t stop_ev;
-        const bool prof = profile_begin(stream, "bomp_warp_kernel", &stop_ev);
-        rc = bomp_greedy_generic(alpha, G, K, C, k, idx + s0 * k, val + s0 * k,
-                                 nsel ? nsel + s0 : nullptr,
-                                 Z ? Z + s0 * zss : nullptr, zas, zss, stream);
+        const bool prof = profile_begin(stream, fast ? "bomp_fast_kernel" : "bomp_warp_kernel", &stop_ev);
+        if (fast)
+            rc = bomp_greedy_fast(alpha, G, K, C, k, idx + s0 * k, val + s0 * k, nsel ? nsel + s0 : nullptr,
+                                  Z ? Z + s0 * zss : nullptr, zss, stream);
+        else
+            rc = bomp_greedy_generic(alpha, G, K, C, k, idx + s0 * k, val + s0 * k,
+                                     nsel ? nsel + s0 : nullptr,
+                                     Z ? Z + s0 * zss : nullptr, zas, zss, stream);
         if (prof) cudaEventRecord(stop_ev, stream);
         if (rc) return rc;
     }
