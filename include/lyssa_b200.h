@@ -93,6 +93,13 @@ LYS_API int lys_bomp_encode(const float* X, int64_t x_feat_stride, int64_t x_sig
                     float* Z, int64_t z_atom_stride, int64_t z_sig_stride,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* The correlation GEMM alone (test/bring-up hook): alpha (C,K) row-major = X^T D.
+ * impl: 0 = what lys_bomp_encode uses, 1 = fp32 SIMT, 2 = tcgen05 bf16x3 (n = 64, K % 256 == 0),
+ * 3 = tcgen05 with the descriptor LBO/SBO fields exchanged (bring-up only). */
+LYS_API int lys_corr_gemm(const float* X, int64_t x_feat_stride, int64_t x_sig_stride,
+                          const float* D, int64_t ldd, int n, int K, int64_t C, float* alpha,
+                          int impl, void* stream);
+
 /* Same call for HOST buffers (what `sparse_encoder.encode(X, D)` is for NumPy arrays):
  * uploads D, forms the Gram matrix, streams X through the device in chunks with copies
  * overlapped with compute, writes idx/val/nsel and/or dense Z back to host memory.

@@ -26,6 +26,7 @@ SIGNATURES = {
     "lys_bomp_workspace_bytes": (c_sz, [c_int, c_int, c_i64, c_int]),
     "lys_bomp_encode": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_i64, c_int,
                                 c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_sz, c_vp]),
+    "lys_corr_gemm": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_i64, c_vp, c_int, c_vp]),
     "lys_bomp_encode_host": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_i64, c_int,
                                      c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int]),
     "lys_codes_to_dense": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_i64, c_vp]),

@@ -6,6 +6,7 @@
 #include <vector>
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 namespace lys {
 
@@ -16,6 +17,10 @@ int bomp_greedy_generic(const float* alpha, const float* G, int K, int64_t C, in
 bool bomp_fast_supported(int K, int k, int64_t zas, bool has_Z, const float* Z, int64_t zss);
 int bomp_greedy_fast(const float* alpha, const float* G, int K, int64_t C, int k,
                      int32_t* idx, float* val, int32_t* nsel, float* Z, int64_t zss, cudaStream_t stream);
+
+bool corr_gemm_tc_supported(int n, int K);
+int corr_gemm_tc(const float* X, int64_t xfs, int64_t xss, const float* D, int64_t ldd,
+                 int n, int K, int64_t C, float* alpha, cudaStream_t stream, int swap_lbo_sbo);
 
 // fused tcgen05 path (bomp_fused.cu); returns LYS_EUNSUPPORTED for shapes it is not built for
 int bomp_encode_fused(const float* X, int64_t xfs, int64_t xss, const float* D, int64_t ldd,
@@ -60,7 +65,9 @@ constexpr int64_t kChunkBytesTarget = 64ll << 20;
 
 int64_t generic_chunk(int K, int64_t N)
 {
-    int64_t c = kChunkBytesTarget / ((int64_t)K * 4);
+    int64_t target = kChunkBytesTarget;
+    if (const char* e = getenv("LYS_CHUNK_MB")) { long v = atol(e); if (v >= 1 && v <= 4096) target = (int64_t)v << 20; }
+    int64_t c = target / ((int64_t)K * 4);
     c = std::max<int64_t>(1024, c / 1024 * 1024);
     return std::min<int64_t>(c, std::max<int64_t>(N, 1));
 }
@@ -133,10 +140,13 @@ extern "C" int lys_bomp_encode(const float* X, int64_t xfs, int64_t xss,
     // generic path: per chunk, Alpha = X_chunk^T D (fp32 GEMM) then one warp per signal
     float* alpha = reinterpret_cast<float*>(workspace);
     const int64_t chunk = generic_chunk(K, N);
+    const char* gemm_env = getenv("LYS_GEMM");
+    const bool use_tc = corr_gemm_tc_supported(n, K) && !(gemm_env && !strcmp(gemm_env, "simt"));
     const bool fast = bomp_fast_supported(K, k, zas, Z != nullptr, Z, zss) && !getenv("LYS_FORCE_GENERIC");
     for (int64_t s0 = 0; s0 < N; s0 += chunk) {
         const int64_t C = std::min(chunk, N - s0);
-        rc = sgemm_strided(X + s0 * xss, xss, xfs, D, ldd, 1, alpha, K, 1, C, K, n, stream);
+        if (use_tc) rc = corr_gemm_tc(X + s0 * xss, xfs, xss, D, ldd, n, K, C, alpha, stream, 0);
+        else rc = sgemm_strided(X + s0 * xss, xss, xfs, D, ldd, 1, alpha, K, 1, C, K, n, stream);
         if (rc) return rc;
         cudaEvent_t stop_ev;
         const bool prof = profile_begin(stream, fast ? "bomp_fast_kernel" : "bomp_warp_kernel", &stop_ev);
@@ -187,6 +197,20 @@ extern "C" int lys_profile_fetch(double* kernel_ms, int64_t* launches, const cha
         g_prof.used.clear();
     }
     return LYS_OK;
+}
+
+extern "C" int lys_corr_gemm(const float* X, int64_t xfs, int64_t xss, const float* D, int64_t ldd,
+                             int n, int K, int64_t C, float* alpha, int impl, void* stream)
+{
+    LYS_CHECK_ARG(X && D && alpha && n >= 1 && K >= 1 && C >= 0 && ldd >= K, "lys_corr_gemm: bad argument");
+    if (impl == 0) impl = corr_gemm_tc_supported(n, K) ? 2 : 1;
+    if (impl == 1) return sgemm_strided(X, xss, xfs, D, ldd, 1, alpha, K, 1, C, K, n, (cudaStream_t)stream);
+    if (impl == 2 || impl == 3) {
+        if (!corr_gemm_tc_supported(n, K)) { set_error("lys_corr_gemm: tcgen05 path needs n=64, K multiple of 256"); return LYS_EUNSUPPORTED; }
+        return corr_gemm_tc(X, xfs, xss, D, ldd, n, K, C, alpha, (cudaStream_t)stream, impl == 3);
+    }
+    set_error("lys_corr_gemm: unknown impl %d", impl);
+    return LYS_EINVAL;
 }
 
 extern "C" int lys_codes_to_dense(const int32_t* idx, const float* val, int64_t N, int k, int K,
