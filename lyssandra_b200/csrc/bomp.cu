@@ -20,7 +20,7 @@ int bomp_greedy_fast(const float* alpha, const float* G, int K, int64_t C, int k
 
 bool corr_gemm_tc_supported(int n, int K);
 int corr_gemm_tc(const float* X, int64_t xfs, int64_t xss, const float* D, int64_t ldd,
-                 int n, int K, int64_t C, float* alpha, cudaStream_t stream, int swap_lbo_sbo);
+                 int n, int K, int64_t C, float* alpha, cudaStream_t stream);
 
 // fused tcgen05 path (bomp_fused.cu); returns LYS_EUNSUPPORTED for shapes it is not built for
 int bomp_encode_fused(const float* X, int64_t xfs, int64_t xss, const float* D, int64_t ldd,
@@ -145,7 +145,7 @@ extern "C" int lys_bomp_encode(const float* X, int64_t xfs, int64_t xss,
     const bool fast = bomp_fast_supported(K, k, zas, Z != nullptr, Z, zss) && !getenv("LYS_FORCE_GENERIC");
     for (int64_t s0 = 0; s0 < N; s0 += chunk) {
         const int64_t C = std::min(chunk, N - s0);
-        if (use_tc) rc = corr_gemm_tc(X + s0 * xss, xfs, xss, D, ldd, n, K, C, alpha, stream, 0);
+        if (use_tc) rc = corr_gemm_tc(X + s0 * xss, xfs, xss, D, ldd, n, K, C, alpha, stream);
         else rc = sgemm_strided(X + s0 * xss, xss, xfs, D, ldd, 1, alpha, K, 1, C, K, n, stream);
         if (rc) return rc;
         cudaEvent_t stop_ev;
@@ -205,9 +205,9 @@ extern "C" int lys_corr_gemm(const float* X, int64_t xfs, int64_t xss, const flo
     LYS_CHECK_ARG(X && D && alpha && n >= 1 && K >= 1 && C >= 0 && ldd >= K, "lys_corr_gemm: bad argument");
     if (impl == 0) impl = corr_gemm_tc_supported(n, K) ? 2 : 1;
     if (impl == 1) return sgemm_strided(X, xss, xfs, D, ldd, 1, alpha, K, 1, C, K, n, (cudaStream_t)stream);
-    if (impl == 2 || impl == 3) {
+    if (impl == 2) {
         if (!corr_gemm_tc_supported(n, K)) { set_error("lys_corr_gemm: tcgen05 path needs n=64, K multiple of 256"); return LYS_EUNSUPPORTED; }
-        return corr_gemm_tc(X, xfs, xss, D, ldd, n, K, C, alpha, (cudaStream_t)stream, impl == 3);
+        return corr_gemm_tc(X, xfs, xss, D, ldd, n, K, C, alpha, (cudaStream_t)stream);
     }
     set_error("lys_corr_gemm: unknown impl %d", impl);
     return LYS_EINVAL;

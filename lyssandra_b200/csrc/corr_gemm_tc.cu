@@ -134,7 +134,7 @@ __device__ __forceinline__ void store_chunk(unsigned char* plane0, int plane_byt
 __global__ void __launch_bounds__(THREADS, 1)
 corr_gemm_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss,
                     const float* __restrict__ D, int64_t ldd,
-                    int K, int64_t C, float* __restrict__ alpha, int swap_lbo_sbo)
+                    int K, int64_t C, float* __restrict__ alpha)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sB = smem;
@@ -213,10 +213,6 @@ corr_gemm_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss,
         if (lane == 0) {
             const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
             constexpr uint32_t LBO_A = TM * 16, LBO_B = TN * 16, SBO = 128;
-            // descriptor fields: (lbo, sbo) = (K-direction stride, 8-row-group stride); `swap_lbo_sbo`
-            // is a bring-up switch that exchanges the two fields (see tests/test_gpu_gemm.py)
-            const uint32_t fa0 = swap_lbo_sbo ? SBO : LBO_A, fa1 = swap_lbo_sbo ? LBO_A : SBO;
-            const uint32_t fb0 = swap_lbo_sbo ? SBO : LBO_B, fb1 = swap_lbo_sbo ? LBO_B : SBO;
             // small products first: (3,1) (2,2) (1,3) (2,1) (1,2) (1,1)   [1-based plane indices]
             const int pa[6] = {2, 1, 0, 1, 0, 0};
             const int pb[6] = {0, 1, 2, 0, 1, 0};
@@ -233,8 +229,8 @@ corr_gemm_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss,
                 for (int p = 0; p < 6; ++p) {
 #pragma unroll
                     for (int ks = 0; ks < NF / 16; ++ks) {
-                        const uint64_t ad = make_desc(a_base + st * A_STAGE + pa[p] * A_PLANE + ks * 2 * LBO_A, fa0, fa1);
-                        const uint64_t bd = make_desc(b_base + pb[p] * B_PLANE + ks * 2 * LBO_B, fb0, fb1);
+                        const uint64_t ad = make_desc(a_base + st * A_STAGE + pa[p] * A_PLANE + ks * 2 * LBO_A, LBO_A, SBO);
+                        const uint64_t bd = make_desc(b_base + pb[p] * B_PLANE + ks * 2 * LBO_B, LBO_B, SBO);
                         tc_mma_bf16(d_tmem, ad, bd, kIdesc, acc);
                         acc = 1;
                     }
@@ -286,7 +282,7 @@ bool corr_gemm_tc_supported(int n, int K)
 
 // Alpha (C, K) row-major fp32 = X^T D for a chunk of C signals
 int corr_gemm_tc(const float* X, int64_t xfs, int64_t xss, const float* D, int64_t ldd,
-                 int n, int K, int64_t C, float* alpha, cudaStream_t stream, int swap_lbo_sbo)
+                 int n, int K, int64_t C, float* alpha, cudaStream_t stream)
 {
     if (!corr_gemm_tc_supported(n, K)) return LYS_EUNSUPPORTED;
     if (C <= 0) return LYS_OK;
@@ -300,7 +296,7 @@ int corr_gemm_tc(const float* X, int64_t xfs, int64_t xss, const float* D, int64
     int groups = sm_count() / n_slices;
     if (groups < 1) groups = 1;
     if ((int64_t)groups > n_tiles) groups = (int)n_tiles;
-    corr_gemm_tc_kernel<<<groups * n_slices, THREADS, SMEM_TOTAL, stream>>>(X, xfs, xss, D, ldd, K, C, alpha, swap_lbo_sbo);
+    corr_gemm_tc_kernel<<<groups * n_slices, THREADS, SMEM_TOTAL, stream>>>(X, xfs, xss, D, ldd, K, C, alpha);
     LYS_LAUNCH_CHECK("corr_gemm_tc_kernel");
     return LYS_OK;
 }
