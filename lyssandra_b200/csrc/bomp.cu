@@ -19,7 +19,9 @@ int bomp_greedy_fast(const float* alpha, const float* G, int K, int64_t C, int k
                      int32_t* idx, float* val, int32_t* nsel, float* Z, int64_t zss, cudaStream_t stream);
 
 bool corr_gemm_tc_supported(int n, int K);
-int corr_gemm_tc(const float* X, int64_t xfs, int64_t xss, const float* D, int64_t ldd,
+size_t corr_gemm_tc_planes_bytes(int n, int K);
+int corr_gemm_tc_prepare(const float* D, int64_t ldd, int n, int K, void* planes, cudaStream_t stream);
+int corr_gemm_tc(const float* X, int64_t xfs, int64_t xss, const void* planes,
                  int n, int K, int64_t C, float* alpha, cudaStream_t stream);
 
 // fused tcgen05 path (bomp_fused.cu); returns LYS_EUNSUPPORTED for shapes it is not built for
@@ -58,10 +60,14 @@ bool profile_begin(cudaStream_t st, const char* name, cudaEvent_t* stop_out)
 
 namespace {
 
-// signals per correlation chunk of the generic path: the (chunk x K) fp32 Alpha tile is
-// written by the GEMM and read once by the greedy kernel; 16384 x 1024 x 4 B = 64 MB stays
-// inside the 126 MB L2, so Alpha costs (almost) no HBM traffic.
-constexpr int64_t kChunkBytesTarget = 64ll << 20;
+constexpr int NF_MAX_HOOK = 64;
+
+// signals per correlation chunk: the (chunk x K) fp32 Alpha tile is written by the GEMM kernel
+// and read once by the greedy kernel.  Measured on B200 (profiles/README.md): per-launch fixed
+// costs (D-plane staging, tail waves) outweigh L2 residency of the tile — 16/64/128/512 MB
+// chunks give 10.8/6.9/6.2/5.5 ms per 1M-patch encode — so the default is 512 MB
+// (LYS_CHUNK_MB overrides for experiments).
+constexpr int64_t kChunkBytesTarget = 512ll << 20;
 
 int64_t generic_chunk(int K, int64_t N)
 {
@@ -104,7 +110,7 @@ using namespace lys;
 extern "C" size_t lys_bomp_workspace_bytes(int n, int K, int64_t N, int k)
 {
     if (n < 1 || K < 1 || N < 0 || k < 1) return 0;
-    size_t generic = (size_t)generic_chunk(K, N) * (size_t)K * sizeof(float) + 256;
+    size_t generic = align_up((size_t)generic_chunk(K, N) * (size_t)K * sizeof(float), 256) + align_up(corr_gemm_tc_planes_bytes(n, K), 256) + 256;
     size_t fused = bomp_fused_workspace_bytes(n, K, N, k);
     return std::max(generic, fused);
 }
@@ -140,12 +146,17 @@ extern "C" int lys_bomp_encode(const float* X, int64_t xfs, int64_t xss,
     // generic path: per chunk, Alpha = X_chunk^T D (fp32 GEMM) then one warp per signal
     float* alpha = reinterpret_cast<float*>(workspace);
     const int64_t chunk = generic_chunk(K, N);
+    void* planes = reinterpret_cast<unsigned char*>(workspace) + align_up((size_t)chunk * (size_t)K * sizeof(float), 256);
     const char* gemm_env = getenv("LYS_GEMM");
     const bool use_tc = corr_gemm_tc_supported(n, K) && !(gemm_env && !strcmp(gemm_env, "simt"));
     const bool fast = bomp_fast_supported(K, k, zas, Z != nullptr, Z, zss) && !getenv("LYS_FORCE_GENERIC");
+    if (use_tc) {
+        rc = corr_gemm_tc_prepare(D, ldd, n, K, planes, stream);
+        if (rc) return rc;
+    }
     for (int64_t s0 = 0; s0 < N; s0 += chunk) {
         const int64_t C = std::min(chunk, N - s0);
-        if (use_tc) rc = corr_gemm_tc(X + s0 * xss, xfs, xss, D, ldd, n, K, C, alpha, stream);
+        if (use_tc) rc = corr_gemm_tc(X + s0 * xss, xfs, xss, planes, n, K, C, alpha, stream);
         else rc = sgemm_strided(X + s0 * xss, xss, xfs, D, ldd, 1, alpha, K, 1, C, K, n, stream);
         if (rc) return rc;
         cudaEvent_t stop_ev;
@@ -169,7 +180,7 @@ extern "C" int lys_bomp_launch_count(int n, int K, int64_t N, int k)
     int fused = bomp_fused_launch_count(n, K, N, k);
     if (fused > 0) return fused;
     const int64_t chunk = generic_chunk(K, N);
-    return (int)(2 * ((N + chunk - 1) / chunk));
+    return (int)(2 * ((N + chunk - 1) / chunk)) + (corr_gemm_tc_supported(n, K) ? 1 : 0);
 }
 
 extern "C" int lys_profile_enable(int on)
@@ -207,7 +218,13 @@ extern "C" int lys_corr_gemm(const float* X, int64_t xfs, int64_t xss, const flo
     if (impl == 1) return sgemm_strided(X, xss, xfs, D, ldd, 1, alpha, K, 1, C, K, n, (cudaStream_t)stream);
     if (impl == 2) {
         if (!corr_gemm_tc_supported(n, K)) { set_error("lys_corr_gemm: tcgen05 path needs n=64, K multiple of 256"); return LYS_EUNSUPPORTED; }
-        return corr_gemm_tc(X, xfs, xss, D, ldd, n, K, C, alpha, (cudaStream_t)stream);
+        static void* hook_planes[64] = {nullptr};          // bring-up hook only: cached per device, never freed
+        int dev = 0;
+        LYS_CUDA(cudaGetDevice(&dev));
+        if (!hook_planes[dev & 63]) LYS_CUDA(cudaMalloc(&hook_planes[dev & 63], corr_gemm_tc_planes_bytes(NF_MAX_HOOK, LYS_MAX_ATOMS)));
+        int rc2 = corr_gemm_tc_prepare(D, ldd, n, K, hook_planes[dev & 63], (cudaStream_t)stream);
+        if (rc2) return rc2;
+        return corr_gemm_tc(X, xfs, xss, hook_planes[dev & 63], n, K, C, alpha, (cudaStream_t)stream);
     }
     set_error("lys_corr_gemm: unknown impl %d", impl);
     return LYS_EINVAL;

@@ -51,6 +51,11 @@ bomp_fast_kernel(const float* __restrict__ alpha, const float* __restrict__ G,
 
     for (int64_t i = warp_global; i < C; i += n_warps) {
         float a[EPL];
+        if (i + n_warps < C) {
+            const char* nxt = reinterpret_cast<const char*>(alpha + (i + n_warps) * (int64_t)K);
+            for (int b = lane * 128; b < K * 4; b += 32 * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + b));
+        }
         {
             const float* arow = alpha + i * (int64_t)K + lane_off;
 #pragma unroll
@@ -80,6 +85,14 @@ bomp_fast_kernel(const float* __restrict__ alpha, const float* __restrict__ G,
             const unsigned gbits = __reduce_max_sync(0xffffffffu, mbits);
             const int pick = (int)__reduce_min_sync(0xffffffffu, mbits == gbits ? (unsigned)bidx : 0x7fffffffu);
             const float apick = __shfl_sync(0xffffffffu, bval, (pick & 127) >> 2);   // alpha_{j-1}[pick], signed
+            // issue the Gram-row gather NOW (address is always valid): its L2 latency overlaps the
+            // scalar Cholesky work below instead of following it
+            float4 g[NV];
+            if (j + 1 < k) {
+                const float* grow = G + (int64_t)pick * K + lane_off;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) g[v] = ldg_f4(grow + 128 * v);
+            }
             // ---- :323-325 already selected -> stop
             bool dup = false;
 #pragma unroll
@@ -117,10 +130,6 @@ bomp_fast_kernel(const float* __restrict__ alpha, const float* __restrict__ G,
 #pragma unroll
             for (int m = 0; m < KNZ; ++m) if (m < j) cm[m] = L[j][m] * dinv[m];
             const float coef = y[j] * di;
-            const float* grow = G + (int64_t)pick * K + lane_off;
-            float4 g[NV];
-#pragma unroll
-            for (int v = 0; v < NV; ++v) g[v] = ldg_f4(grow + 128 * v);
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
                 float4 t = g[v];

@@ -1,16 +1,70 @@
 // comm.cu — peer-mapped exchange buffers for the multi-rank K-SVD sweep (one process per GPU).
-// Placeholder: creation succeeds for world == 1 only until the P2P path lands.
-#include "common.cuh"
+// Each rank cudaMalloc's one small buffer, exports its CUDA IPC handle (64 bytes); the host
+// (torch.distributed all_gather) hands every rank all handles; peers are opened with
+// cudaIpcOpenMemHandle, which maps them over NVLink/NVSwitch.  The sweep kernel then writes its
+// per-atom partial sums straight into every peer's buffer and polls flags in its own.
+#include "comm.cuh"
+#include <string.h>
+
+using namespace lys;
+
+static_assert(sizeof(cudaIpcMemHandle_t) == LYS_COMM_HANDLE_BYTES, "IPC handle size");
 
 extern "C" int lys_comm_create(int rank, int world, void** comm)
 {
     LYS_CHECK_ARG(comm, "lys_comm_create: null out pointer");
-    LYS_CHECK_ARG(world >= 1 && rank >= 0 && rank < world, "lys_comm_create: bad rank/world");
+    LYS_CHECK_ARG(world >= 1 && world <= COMM_MAX_RANKS && rank >= 0 && rank < world,
+                  "lys_comm_create: bad rank/world (%d/%d, max %d ranks)", rank, world, COMM_MAX_RANKS);
     *comm = nullptr;
-    if (world == 1) return LYS_OK;
-    lys::set_error("lys_comm_create: multi-rank exchange not available in this build");
-    return LYS_EUNSUPPORTED;
+    if (world == 1) return LYS_OK;             // NULL comm == single rank
+    CommHost* h = new CommHost();
+    h->rank = rank; h->world = world;
+    LYS_CUDA(cudaGetDevice(&h->device));
+    LYS_CUDA(cudaMalloc(&h->local, COMM_BUFFER_BYTES));
+    LYS_CUDA(cudaMemset(h->local, 0, COMM_BUFFER_BYTES));
+    LYS_CUDA(cudaDeviceSynchronize());
+    h->peer[rank] = h->local;
+    *comm = h;
+    return LYS_OK;
 }
-extern "C" int lys_comm_export(void*, unsigned char*) { lys::set_error("lys_comm_export: not available"); return LYS_EUNSUPPORTED; }
-extern "C" int lys_comm_connect(void*, const unsigned char*) { lys::set_error("lys_comm_connect: not available"); return LYS_EUNSUPPORTED; }
-extern "C" int lys_comm_destroy(void*) { return LYS_OK; }
+
+extern "C" int lys_comm_export(void* comm, unsigned char handle[LYS_COMM_HANDLE_BYTES])
+{
+    LYS_CHECK_ARG(comm && handle, "lys_comm_export: null argument");
+    CommHost* h = reinterpret_cast<CommHost*>(comm);
+    cudaIpcMemHandle_t ipc;
+    LYS_CUDA(cudaIpcGetMemHandle(&ipc, h->local));
+    memcpy(handle, &ipc, LYS_COMM_HANDLE_BYTES);
+    return LYS_OK;
+}
+
+extern "C" int lys_comm_connect(void* comm, const unsigned char* all_handles)
+{
+    LYS_CHECK_ARG(comm && all_handles, "lys_comm_connect: null argument");
+    CommHost* h = reinterpret_cast<CommHost*>(comm);
+    for (int r = 0; r < h->world; ++r) {
+        if (r == h->rank) continue;
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, all_handles + (size_t)r * LYS_COMM_HANDLE_BYTES, LYS_COMM_HANDLE_BYTES);
+        LYS_CUDA(cudaIpcOpenMemHandle(&h->peer[r], ipc, cudaIpcMemLazyEnablePeerAccess));
+    }
+    h->dev.rank = h->rank; h->dev.world = h->world;
+    for (int r = 0; r < COMM_MAX_RANKS; ++r) {
+        void* base = r < h->world ? h->peer[r] : nullptr;
+        h->dev.slots[r] = reinterpret_cast<float*>(base);
+        h->dev.flags[r] = base ? reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(base) + COMM_FLAG_OFFSET_BYTES) : nullptr;
+    }
+    h->connected = true;
+    return LYS_OK;
+}
+
+extern "C" int lys_comm_destroy(void* comm)
+{
+    if (!comm) return LYS_OK;
+    CommHost* h = reinterpret_cast<CommHost*>(comm);
+    for (int r = 0; r < h->world; ++r)
+        if (r != h->rank && h->peer[r]) cudaIpcCloseMemHandle(h->peer[r]);
+    if (h->local) cudaFree(h->local);
+    delete h;
+    return LYS_OK;
+}

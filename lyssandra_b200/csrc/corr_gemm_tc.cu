@@ -38,7 +38,9 @@ constexpr int A_STAGE = 3 * A_PLANE;       // 48 KB
 constexpr int SMEM_B = 3 * B_PLANE;        // 96 KB
 constexpr int SMEM_A = 2 * A_STAGE;        // 96 KB
 constexpr int SMEM_BAR = 128;
-constexpr int SMEM_TOTAL = SMEM_B + SMEM_A + SMEM_BAR;
+constexpr int EPI_LD = 33;                          // padded row of the per-warp 32x32 transpose tile
+constexpr int SMEM_EPI = 4 * 32 * EPI_LD * 4;       // 16.5 KB
+constexpr int SMEM_TOTAL = SMEM_B + SMEM_A + SMEM_BAR + SMEM_EPI;
 constexpr int THREADS = 288;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -133,7 +135,7 @@ __device__ __forceinline__ void store_chunk(unsigned char* plane0, int plane_byt
 
 __global__ void __launch_bounds__(THREADS, 1)
 corr_gemm_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss,
-                    const float* __restrict__ D, int64_t ldd,
+                    const uint4* __restrict__ planes /* per 256-atom slice: 3 planes in smem layout */,
                     int K, int64_t C, float* __restrict__ alpha)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -142,6 +144,7 @@ corr_gemm_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss,
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_B + SMEM_A);
     // bars[0..1] a_full, [2..3] a_empty, [4..5] acc_full, [6..7] acc_empty, then the TMEM base
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    float* sEpi = reinterpret_cast<float*>(smem + SMEM_B + SMEM_A + SMEM_BAR);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_slices = K / TN;
@@ -162,13 +165,12 @@ corr_gemm_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss,
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    // B planes: this CTA's 256 atoms x 64 features, resident for the whole kernel
-    for (int item = tid; item < TN * (NF / 8); item += THREADS) {
-        const int atom = item % TN, kc = item / TN;
-        float v[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = __ldg(D + (int64_t)(kc * 8 + e) * ldd + a0 + atom);
-        store_chunk(sB, B_PLANE, kc * (TN * 16) + atom * 16, v);
+    // B planes: this CTA's 256 atoms x 64 features (pre-split by split_dict_planes_kernel),
+    // 96 KB copied once and resident for the whole kernel
+    {
+        const uint4* src = planes + (size_t)slice * (SMEM_B / 16);
+        uint4* dst = reinterpret_cast<uint4*>(sB);
+        for (int item = tid; item < SMEM_B / 16; item += THREADS) dst[item] = __ldg(src + item);
     }
     fence_async_smem();
     tc_fence_before();
@@ -187,24 +189,20 @@ corr_gemm_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss,
             unsigned char* dst = sA + st * A_STAGE;
             const bool ok = sig < C;
             const float* xp = X + sig * xss;
+            float xin[NF];
+            if (xfs == 1) {
 #pragma unroll
-            for (int kc = 0; kc < NF / 8; ++kc) {
-                float v[8];
-                if (xfs == 1) {
-                    if (ok) {
-                        const float4 lo = __ldg(reinterpret_cast<const float4*>(xp + kc * 8));
-                        const float4 hi = __ldg(reinterpret_cast<const float4*>(xp + kc * 8 + 4));
-                        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = 0.f;
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = ok ? __ldg(xp + (int64_t)(kc * 8 + e) * xfs) : 0.f;
+                for (int q = 0; q < NF / 4; ++q) {
+                    const float4 v4 = ok ? __ldg(reinterpret_cast<const float4*>(xp) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    xin[4 * q] = v4.x; xin[4 * q + 1] = v4.y; xin[4 * q + 2] = v4.z; xin[4 * q + 3] = v4.w;
                 }
-                store_chunk(dst, A_PLANE, kc * (TM * 16) + row * 16, v);
+            } else {
+#pragma unroll
+                for (int f = 0; f < NF; ++f) xin[f] = ok ? __ldg(xp + (int64_t)f * xfs) : 0.f;
             }
+#pragma unroll
+            for (int kc = 0; kc < NF / 8; ++kc)
+                store_chunk(dst, A_PLANE, kc * (TM * 16) + row * 16, xin + kc * 8);
             fence_async_smem();
             mbar_arrive(smem_u32(&bars[0 + st]));
         }
@@ -247,19 +245,22 @@ corr_gemm_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss,
             const int st = it & 1;
             mbar_wait(smem_u32(&bars[4 + st]), (it >> 1) & 1);
             tc_fence_after();
-            const int64_t sig = t * TM + warp * 32 + lane;
-            float* out = alpha + sig * (int64_t)K + a0;
+            const int64_t sig0 = t * TM + warp * 32;
+            float* tile = sEpi + warp * 32 * EPI_LD;
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(st * TN);
 #pragma unroll 1
             for (int c = 0; c < TN / 32; ++c) {
                 uint32_t r[32];
                 TMEM_LD_32x32b_x32(taddr + c * 32, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (sig < C) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        *reinterpret_cast<uint4*>(out + c * 32 + q * 4) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
-                }
+                for (int q = 0; q < 32; ++q) tile[lane * EPI_LD + q] = __uint_as_float(r[q]);   // lane = signal row
+                __syncwarp();
+                float* out = alpha + sig0 * (int64_t)K + a0 + c * 32 + lane;
+#pragma unroll 8
+                for (int rr = 0; rr < 32; ++rr)
+                    if (sig0 + rr < C) out[(int64_t)rr * K] = tile[rr * EPI_LD + lane];          // 128 B per store
+                __syncwarp();
             }
             tc_fence_before();
             mbar_arrive(smem_u32(&bars[6 + st]));
@@ -273,6 +274,19 @@ corr_gemm_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss,
     }
 }
 
+// D (n=64, K) fp32 -> for every 256-atom slice, the three bf16 planes in the kernel's smem layout
+__global__ void split_dict_planes_kernel(const float* __restrict__ D, int64_t ldd, int K, unsigned char* __restrict__ planes)
+{
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;        // one 16-byte chunk of one atom
+    if (item >= K * (NF / 8)) return;
+    const int atom = item % K, kc = item / K;
+    const int slice = atom / TN, a_local = atom % TN;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = __ldg(D + (int64_t)(kc * 8 + e) * ldd + atom);
+    store_chunk(planes + (size_t)slice * SMEM_B, B_PLANE, kc * (TN * 16) + a_local * 16, v);
+}
+
 }  // namespace
 
 bool corr_gemm_tc_supported(int n, int K)
@@ -280,8 +294,19 @@ bool corr_gemm_tc_supported(int n, int K)
     return n == NF && K >= TN && (K % TN) == 0 && K <= LYS_MAX_ATOMS;
 }
 
-// Alpha (C, K) row-major fp32 = X^T D for a chunk of C signals
-int corr_gemm_tc(const float* X, int64_t xfs, int64_t xss, const float* D, int64_t ldd,
+size_t corr_gemm_tc_planes_bytes(int n, int K) { return corr_gemm_tc_supported(n, K) ? (size_t)(K / TN) * SMEM_B : 0; }
+
+int corr_gemm_tc_prepare(const float* D, int64_t ldd, int n, int K, void* planes, cudaStream_t stream)
+{
+    if (!corr_gemm_tc_supported(n, K)) return LYS_EUNSUPPORTED;
+    const int items = K * (NF / 8);
+    split_dict_planes_kernel<<<(items + 255) / 256, 256, 0, stream>>>(D, ldd, K, reinterpret_cast<unsigned char*>(planes));
+    LYS_LAUNCH_CHECK("split_dict_planes_kernel");
+    return LYS_OK;
+}
+
+// Alpha (C, K) row-major fp32 = X^T D for a chunk of C signals; `planes` from corr_gemm_tc_prepare
+int corr_gemm_tc(const float* X, int64_t xfs, int64_t xss, const void* planes,
                  int n, int K, int64_t C, float* alpha, cudaStream_t stream)
 {
     if (!corr_gemm_tc_supported(n, K)) return LYS_EUNSUPPORTED;
@@ -296,7 +321,7 @@ int corr_gemm_tc(const float* X, int64_t xfs, int64_t xss, const float* D, int64
     int groups = sm_count() / n_slices;
     if (groups < 1) groups = 1;
     if ((int64_t)groups > n_tiles) groups = (int)n_tiles;
-    corr_gemm_tc_kernel<<<groups * n_slices, THREADS, SMEM_TOTAL, stream>>>(X, xfs, xss, D, ldd, K, C, alpha);
+    corr_gemm_tc_kernel<<<groups * n_slices, THREADS, SMEM_TOTAL, stream>>>(X, xfs, xss, reinterpret_cast<const uint4*>(planes), K, C, alpha);
     LYS_LAUNCH_CHECK("corr_gemm_tc_kernel");
     return LYS_OK;
 }

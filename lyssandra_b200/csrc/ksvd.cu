@@ -38,6 +38,8 @@ __global__ void transpose_kernel(const float* __restrict__ src, int64_t lds, flo
     }
 }
 
+}  // namespace
+
 int transpose(const float* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, cudaStream_t st)
 {
     dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
@@ -45,6 +47,8 @@ int transpose(const float* src, int64_t lds, float* dst, int64_t ldd, int rows, 
     LYS_LAUNCH_CHECK("transpose_kernel");
     return LYS_OK;
 }
+
+namespace {
 
 // ------------------------------------------------------------------------- residual
 constexpr int RES_WARPS = 8;
@@ -237,180 +241,6 @@ csr_fill_kernel(const int32_t* __restrict__ idx, const float* __restrict__ val, 
     }
 }
 
-// ------------------------------------------------------------------------------ sweep
-struct PeerComm {           // see comm.cu
-    int rank, world;
-    float* slots[8];        // slots[r] -> rank r's exchange buffer (peer-mapped), layout below
-    unsigned* flags[8];
-};
-
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
-{
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// monotonic-counter grid barrier; requires all CTAs co-resident (cooperative launch)
-__device__ __forceinline__ void grid_barrier(unsigned* counter)
-{
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned nb = gridDim.x;
-        const unsigned old = atomicAdd(counter, 1u);
-        const unsigned target = (old / nb + 1u) * nb;
-        while (ld_acquire_u32(counter) < target) { __nanosleep(20); }
-        __threadfence();
-    }
-    __syncthreads();
-}
-
-constexpr int SW_WARPS = 32;
-
-template <int NPL>
-__global__ void __launch_bounds__(SW_WARPS * 32, 1)
-ksvd_sweep_kernel(float* __restrict__ R, float* __restrict__ Dt,
-                  float* __restrict__ val,
-                  const int32_t* __restrict__ rowptr, const int32_t* __restrict__ entries,
-                  int n, int K, int k, int n_cycles,
-                  int32_t* __restrict__ unused, float* __restrict__ partial /* [grid][n+1] */,
-                  unsigned* __restrict__ barrier)
-{
-    extern __shared__ float sm[];
-    float* d_old = sm;                       // [n]
-    float* d_new = d_old + n;                // [n]
-    float* svec = d_new + n;                 // [n + 1]
-    float* red = svec + (n + 1);             // [SW_WARPS][n + 1]
-    __shared__ float s_scal[2];              // g = d_old . d_new ; (unused)
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int ldr = n + 1;
-    const int64_t gw = (int64_t)blockIdx.x * SW_WARPS + warp;
-    const int64_t gstride = (int64_t)gridDim.x * SW_WARPS;
-
-    for (int cyc = 0; cyc < n_cycles; ++cyc) {
-        for (int c = 0; c < K; ++c) {
-            const int lo = rowptr[c], hi = rowptr[c + 1];
-            if (hi == lo) {                                  // ksvd.py:112-115
-                if (blockIdx.x == 0 && t == 0) unused[c] = 1;
-                continue;
-            }
-            for (int f = t; f < n; f += blockDim.x) d_old[f] = Dt[(int64_t)c * n + f];
-            // ---- phase 1: partial s = sum_i R[i,:] x_i,  sxx = sum x_i^2     (ksvd.py:116-118)
-            float acc[NPL];
-#pragma unroll
-            for (int q = 0; q < NPL; ++q) acc[q] = 0.f;
-            float sxx = 0.f;
-            for (int64_t p = lo + gw; p < hi; p += gstride) {
-                const int ent = entries[p];
-                const int64_t i = ent / k;
-                const float x = val[ent];
-                const float* r = R + i * n;
-#pragma unroll
-                for (int q = 0; q < NPL; ++q) {
-                    int f = lane + 32 * q;
-                    if (f < n) acc[q] = fmaf(r[f], x, acc[q]);
-                }
-                sxx = fmaf(x, x, sxx);
-            }
-#pragma unroll
-            for (int q = 0; q < NPL; ++q) {
-                int f = lane + 32 * q;
-                if (f < n) red[warp * ldr + f] = acc[q];
-            }
-            if (lane == 0) red[warp * ldr + n] = sxx;
-            __syncthreads();
-            if (t <= n) {
-                double s = 0.0;
-                for (int w = 0; w < SW_WARPS; ++w) s += (double)red[w * ldr + t];
-                partial[(int64_t)blockIdx.x * ldr + t] = (float)s;
-            }
-            grid_barrier(barrier);
-            // ---- every CTA: fixed-order sum over CTAs, new atom                (ksvd.py:118-119)
-            if (t <= n) {
-                double s = 0.0;
-                for (unsigned b = 0; b < gridDim.x; ++b) s += (double)partial[(int64_t)b * ldr + t];
-                svec[t] = (float)s;
-            }
-            __syncthreads();
-            if (warp == 0) {
-                const float sxx_all = svec[n];
-                float sv[NPL], dsq = 0.f;
-#pragma unroll
-                for (int q = 0; q < NPL; ++q) {
-                    int f = lane + 32 * q;
-                    sv[q] = (f < n) ? fmaf(d_old[f], sxx_all, svec[f]) : 0.f;   // R_k x = R x + d (x.x)
-                    dsq = fmaf(sv[q], sv[q], dsq);
-                }
-                dsq = warp_sum(dsq);
-                const float inv = 1.f / (sqrtf(dsq) + kRefEps);                    // utils/math.py:61-62
-                float g = 0.f;
-#pragma unroll
-                for (int q = 0; q < NPL; ++q) {
-                    int f = lane + 32 * q;
-                    if (f < n) {
-                        float dn = sv[q] * inv;
-                        d_new[f] = dn;
-                        g = fmaf(d_old[f], dn, g);
-                        if (blockIdx.x == 0) Dt[(int64_t)c * n + f] = dn;
-                    }
-                }
-                g = warp_sum(g);
-                if (lane == 0) s_scal[0] = g;
-            }
-            __syncthreads();
-            const float g = s_scal[0];
-            // ---- phase 2: x' = R_k^T d' ; R <- R_k - d' x'                      (ksvd.py:121-123)
-            float dn[NPL], dold[NPL];
-#pragma unroll
-            for (int q = 0; q < NPL; ++q) {
-                int f = lane + 32 * q;
-                dn[q] = (f < n) ? d_new[f] : 0.f;
-                dold[q] = (f < n) ? d_old[f] : 0.f;
-            }
-            for (int64_t p = lo + gw; p < hi; p += gstride) {
-                const int ent = entries[p];
-                const int64_t i = ent / k;
-                const float x = val[ent];
-                float* r = R + i * n;
-                float rv[NPL], dot = 0.f;
-#pragma unroll
-                for (int q = 0; q < NPL; ++q) {
-                    int f = lane + 32 * q;
-                    rv[q] = (f < n) ? r[f] : 0.f;
-                    dot = fmaf(rv[q], dn[q], dot);
-                }
-                dot = warp_sum(dot);
-                const float xn = fmaf(x, g, dot);
-#pragma unroll
-                for (int q = 0; q < NPL; ++q) {
-                    int f = lane + 32 * q;
-                    if (f < n) r[f] = fmaf(-dn[q], xn, fmaf(dold[q], x, rv[q]));
-                }
-                __syncwarp();
-                if (lane == 0) val[ent] = xn;
-            }
-            grid_barrier(barrier);
-        }
-    }
-}
-
-template <int NPL>
-int launch_sweep(float* R, float* Dt, float* val, const int32_t* rowptr, const int32_t* entries,
-                 int n, int K, int k, int n_cycles, int32_t* unused, float* partial, unsigned* barrier,
-                 int grid, cudaStream_t stream)
-{
-    auto kern = ksvd_sweep_kernel<NPL>;
-    size_t smem = sizeof(float) * (size_t)(2 * n + (n + 1) + SW_WARPS * (n + 1));
-    LYS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    LYS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SW_WARPS * 32, smem));
-    if (per_sm < 1) { set_error("ksvd sweep kernel does not fit on an SM"); return LYS_ECUDA; }
-    void* args[] = {&R, &Dt, &val, &rowptr, &entries, &n, &K, &k, &n_cycles, &unused, &partial, &barrier};
-    LYS_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(SW_WARPS * 32), args, smem, stream));
-    return LYS_OK;
-}
-
 // ------------------------------------------------------------------ norm_cols / gather
 __global__ void norm_cols_kernel(float* __restrict__ D, int64_t ldd, int n, int K)
 {
@@ -506,41 +336,6 @@ extern "C" int lys_build_atom_csr(const int32_t* idx, const float* val, int64_t 
     csr_fill_kernel<<<nw / CSR_WARPS, CSR_WARPS * 32, smem, stream>>>(idx, val, E, K, per_warp, hist, rowptr, entries);
     LYS_LAUNCH_CHECK("csr_fill_kernel");
     return LYS_OK;
-}
-
-extern "C" size_t lys_ksvd_sweep_workspace_bytes(int n, int K)
-{
-    return align_up((size_t)n * K * 4, 256) + align_up((size_t)1024 * (n + 1) * 4, 256) + 256;
-}
-
-extern "C" int lys_approx_ksvd_sweep(float* R, float* D, int64_t ldd, const int32_t* idx, float* val,
-                                     const int32_t* rowptr, const int32_t* entries,
-                                     int n, int K, int64_t N, int k, int n_cycles,
-                                     int32_t* unused, void* comm, void* workspace, size_t workspace_bytes,
-                                     void* stream_)
-{
-    cudaStream_t stream = (cudaStream_t)stream_;
-    (void)idx; (void)N;
-    LYS_CHECK_ARG(R && D && val && rowptr && entries && unused && workspace, "lys_approx_ksvd_sweep: null pointer");
-    LYS_CHECK_ARG(n >= 1 && n <= LYS_MAX_FEATURES && K >= 1 && K <= LYS_MAX_ATOMS && ldd >= K && k >= 1 && n_cycles >= 1,
-                  "lys_approx_ksvd_sweep: bad shape");
-    if (comm) { set_error("lys_approx_ksvd_sweep: multi-rank comm not available in this build"); return LYS_EUNSUPPORTED; }
-    if (workspace_bytes < lys_ksvd_sweep_workspace_bytes(n, K)) { set_error("lys_approx_ksvd_sweep: workspace too small"); return LYS_EWORKSPACE; }
-    unsigned char* p = reinterpret_cast<unsigned char*>(workspace);
-    float* Dt = reinterpret_cast<float*>(p); p += align_up((size_t)n * K * 4, 256);
-    float* partial = reinterpret_cast<float*>(p); p += align_up((size_t)1024 * (n + 1) * 4, 256);
-    unsigned* barrier = reinterpret_cast<unsigned*>(p);
-    LYS_CUDA(cudaMemsetAsync(barrier, 0, 256, stream));
-    LYS_CUDA(cudaMemsetAsync(unused, 0, sizeof(int32_t) * (size_t)K, stream));
-    int rc = transpose(D, ldd, Dt, n, n, K, stream);
-    if (rc) return rc;
-    const int grid = std::min(sm_count(), 1024);
-    if (n <= 32) rc = launch_sweep<1>(R, Dt, val, rowptr, entries, n, K, k, n_cycles, unused, partial, barrier, grid, stream);
-    else if (n <= 64) rc = launch_sweep<2>(R, Dt, val, rowptr, entries, n, K, k, n_cycles, unused, partial, barrier, grid, stream);
-    else if (n <= 128) rc = launch_sweep<4>(R, Dt, val, rowptr, entries, n, K, k, n_cycles, unused, partial, barrier, grid, stream);
-    else rc = launch_sweep<8>(R, Dt, val, rowptr, entries, n, K, k, n_cycles, unused, partial, barrier, grid, stream);
-    if (rc) return rc;
-    return transpose(Dt, n, D, ldd, K, n, stream);
 }
 
 extern "C" int lys_norm_cols(float* D, int64_t ldd, int n, int K, void* stream)

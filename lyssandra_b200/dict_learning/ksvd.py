@@ -19,8 +19,10 @@ from .. import engine
 from .utils import init_dictionary
 
 
-def approx_ksvd(Y, D, X, n_cycles=1, verbose=True):
+def approx_ksvd(Y, D, X, n_cycles=1, verbose=True, comm=None):
     """approx_ksvd(Y, D, X) -> (D, X, unused_atoms), D and X mutated in place (ksvd.py:98-126).
+    ``comm`` (distributed.PeerExchange.handle) makes the per-atom sums global when Y holds only
+    this rank's shard of the signals.
 
     Y: (n, N) CUDA tensor; D: (n, K) CUDA tensor; X: engine.SparseCodes (the sparse form of
     the reference's dense Z; its ``val`` is refreshed in place, the support never changes)."""
@@ -28,17 +30,23 @@ def approx_ksvd(Y, D, X, n_cycles=1, verbose=True):
         raise TypeError("approx_ksvd takes engine.SparseCodes (use sparse_encoder.encode_sparse)")
     R, _ = engine.residual(Y, D, X, want_residual=True, want_error=False)         # :103
     rowptr, entries = engine.build_atom_csr(X)                                      # :111
-    flags = engine.approx_ksvd_sweep(R, D, X, rowptr, entries, n_cycles=n_cycles)   # :105-124
+    flags = engine.approx_ksvd_sweep(R, D, X, rowptr, entries, n_cycles=n_cycles, comm=comm)   # :105-124
     unused_atoms = torch.nonzero(flags).flatten().cpu().tolist()
     return D, X, unused_atoms
 
 
 def ksvd_dict_learn(X, n_atoms, init_dict="data", sparse_coder=None, max_iter=20, non_neg=False,
                     approx=False, eta=None, n_cycles=1, n_jobs=1, mmap=False, verbose=True,
-                    return_codes=False, history=None):
+                    return_codes=False, history=None, dist=None, exchange=None):
     """ksvd_dict_learn(...) -> (D, Z) (ksvd.py:129-231).  Z is dense (K, N) like the
     reference's unless ``return_codes`` (then engine.SparseCodes).  ``history`` (list)
-    receives one dict per iteration: error, n_unused, t_encode, t_update (seconds)."""
+    receives one dict per iteration: error, n_unused, t_encode, t_update (seconds).
+
+    Multi-GPU (one process per GPU): pass ``dist`` (distributed.DistContext) and ``exchange``
+    (distributed.PeerExchange); X is then THIS rank's contiguous shard of the signals, D is
+    replicated.  Encode needs no collective; the sweep all-reduces its per-atom sums inside the
+    kernel; the error is one scalar all-reduce; 'data' initialisation and unused-atom
+    replacement draw from rank 0's shard and are broadcast."""
     if not approx:
         raise NotImplementedError("exact K-SVD (approx=False) is outside this engine's scope; pass approx=True")
     if non_neg:
@@ -49,11 +57,20 @@ def ksvd_dict_learn(X, n_atoms, init_dict="data", sparse_coder=None, max_iter=20
     Xd = engine.as_device_matrix(X, None if numpy_in else X.device)
     dev = Xd.device
 
+    multi = dist is not None and dist.world > 1
+    comm = exchange.handle if (multi and exchange is not None) else None
+    if multi and comm is None:
+        raise ValueError("sharded K-SVD needs a distributed.PeerExchange (exchange=...)")
     unused_data = np.empty((0,), dtype=np.int64)
     if isinstance(init_dict, str):
         if init_dict != "data":
             raise NotImplementedError("init_dict must be 'data' or an (n, K) array")
-        D, unused_data = init_dictionary(Xd, n_atoms, method="data", return_unused_data=True)   # :151-153
+        if not multi or dist.rank == 0:
+            D, unused_data = init_dictionary(Xd, n_atoms, method="data", return_unused_data=True)   # :151-153
+        else:
+            D = torch.empty((Xd.shape[0], n_atoms), dtype=torch.float32, device=dev)
+        if multi:
+            dist.broadcast_(D, src=0)
     else:
         D = engine.as_dictionary(init_dict, dev).clone()                                        # :155 np.copy
     if mmap:
@@ -71,16 +88,20 @@ def ksvd_dict_learn(X, n_atoms, init_dict="data", sparse_coder=None, max_iter=20
         if verbose:
             torch.cuda.synchronize(dev)
         t1 = time.perf_counter()
-        D, _, unused_atoms = approx_ksvd(Xd, D, codes, n_cycles=n_cycles)                       # :186
+        D, _, unused_atoms = approx_ksvd(Xd, D, codes, n_cycles=n_cycles, comm=comm)            # :186
         for slot in unused_atoms:                                                               # :199-207
-            if len(unused_data) == 0:
+            if len(unused_data) == 0 or (multi and dist.rank != 0):
                 break
             pos = np.random.choice(len(unused_data), size=1)[0]
             col = int(unused_data[pos])
             engine.gather_cols_(Xd, [col], D, dst_cols=[slot])
             engine.norm_cols_(D[:, slot:slot + 1])
             unused_data = np.delete(unused_data, pos)
+        if multi and len(unused_atoms) > 0:
+            dist.broadcast_(D, src=0)
         _, err = engine.residual(Xd, D, codes, want_residual=False, want_error=True)            # :220
+        if multi:
+            dist.allreduce_sum_(err)
         error_curr = float(err.item())
         t2 = time.perf_counter()
         if history is not None:

@@ -73,3 +73,37 @@ class DistContext(object):
         out = [None] * self.world
         dist.all_gather_object(out, payload, group=self.group)
         return out
+
+
+class PeerExchange(object):
+    """Peer-mapped exchange buffers for the in-kernel per-atom all-reduce of the K-SVD sweep
+    (lys_comm_* in include/lyssa_b200.h): every rank creates its buffer, the 64-byte CUDA IPC
+    handles are all-gathered through torch.distributed, and each rank maps its peers' buffers.
+    ``handle`` is the opaque pointer to pass as ``comm`` to engine.approx_ksvd_sweep."""
+
+    def __init__(self, ctx: DistContext):
+        import ctypes
+        from . import _native as nat
+        self.ctx = ctx
+        self.handle = None
+        if ctx.world == 1:
+            return
+        lib = nat.load()
+        out = ctypes.c_void_p()
+        nat.check(lib.lys_comm_create(ctx.rank, ctx.world, ctypes.byref(out)))
+        self.handle = out.value
+        buf = (ctypes.c_ubyte * nat.COMM_HANDLE_BYTES)()
+        nat.check(lib.lys_comm_export(ctypes.c_void_p(self.handle), buf))
+        handles = ctx.allgather_bytes(bytes(buf))
+        blob = b"".join(handles)
+        arr = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
+        nat.check(lib.lys_comm_connect(ctypes.c_void_p(self.handle), arr))
+        ctx.barrier()
+
+    def close(self):
+        if self.handle is not None:
+            from . import _native as nat
+            torch.cuda.synchronize()
+            self.ctx.barrier()
+            nat.load().lys_comm_destroy(__import__("ctypes").c_void_p(self.handle))
+            self.handle = None
