@@ -68,7 +68,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
+    path = os.environ.get("LYSSA_B200_LIB") or _build.LIB_PATH          # override: debugging builds only
     if not os.path.isfile(path) or os.environ.get("LYSSA_B200_REBUILD"):
         path = _build.build()
     lib = ctypes.CDLL(path)

@@ -38,9 +38,7 @@ constexpr int A_STAGE = 3 * A_PLANE;       // 48 KB
 constexpr int SMEM_B = 3 * B_PLANE;        // 96 KB
 constexpr int SMEM_A = 2 * A_STAGE;        // 96 KB
 constexpr int SMEM_BAR = 128;
-constexpr int EPI_LD = 33;                          // padded row of the per-warp 32x32 transpose tile
-constexpr int SMEM_EPI = 4 * 32 * EPI_LD * 4;       // 16.5 KB
-constexpr int SMEM_TOTAL = SMEM_B + SMEM_A + SMEM_BAR + SMEM_EPI;
+constexpr int SMEM_TOTAL = SMEM_B + SMEM_A + SMEM_BAR;
 constexpr int THREADS = 288;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -144,7 +142,6 @@ corr_gemm_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss,
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_B + SMEM_A);
     // bars[0..1] a_full, [2..3] a_empty, [4..5] acc_full, [6..7] acc_empty, then the TMEM base
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-    float* sEpi = reinterpret_cast<float*>(smem + SMEM_B + SMEM_A + SMEM_BAR);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_slices = K / TN;
@@ -245,22 +242,21 @@ corr_gemm_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss,
             const int st = it & 1;
             mbar_wait(smem_u32(&bars[4 + st]), (it >> 1) & 1);
             tc_fence_after();
-            const int64_t sig0 = t * TM + warp * 32;
-            float* tile = sEpi + warp * 32 * EPI_LD;
+            // every thread owns one signal row and writes whole 128-byte lines of it (8 x 16 B);
+            // measured faster than a shared-memory transpose to 512-byte warp-contiguous stores
+            const int64_t sig = t * TM + warp * 32 + lane;
+            float* out = alpha + sig * (int64_t)K + a0;
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(st * TN);
 #pragma unroll 1
             for (int c = 0; c < TN / 32; ++c) {
                 uint32_t r[32];
                 TMEM_LD_32x32b_x32(taddr + c * 32, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (sig < C) {
 #pragma unroll
-                for (int q = 0; q < 32; ++q) tile[lane * EPI_LD + q] = __uint_as_float(r[q]);   // lane = signal row
-                __syncwarp();
-                float* out = alpha + sig0 * (int64_t)K + a0 + c * 32 + lane;
-#pragma unroll 8
-                for (int rr = 0; rr < 32; ++rr)
-                    if (sig0 + rr < C) out[(int64_t)rr * K] = tile[rr * EPI_LD + lane];          // 128 B per store
-                __syncwarp();
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<uint4*>(out + c * 32 + q * 4) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+                }
             }
             tc_fence_before();
             mbar_arrive(smem_u32(&bars[6 + st]));

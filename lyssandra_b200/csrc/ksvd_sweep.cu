@@ -98,6 +98,10 @@ ksvd_sweep_kernel(float* __restrict__ R, float* __restrict__ Dt, float* __restri
             const int local_count = rowptr[c + 1] - rowptr[c];
             if (pc.world == 1 && local_count == 0) {         // ksvd.py:112-115
                 if (b == 0 && t == 0) unused[c] = 1;
+                // the one-thread store above diverges warp 0; without an explicit reconvergence the
+                // `continue` let its lanes reach the next bar.sync separately (found by
+                // compute-sanitizer racecheck: barrier phases slipped after every unused atom)
+                __syncwarp();
                 continue;
             }
             ++seq;
