@@ -30,10 +30,10 @@ namespace {
 
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-template <int EPL> struct FastCfg { static constexpr int kMaxWarps = (EPL >= 64) ? 8 : 16; };
+template <int EPL, int KNZ> struct FastCfg { static constexpr int kMaxWarps = (EPL >= 64 || KNZ > 5) ? 8 : 16; };
 
 template <int EPL, int KNZ>
-__global__ void __launch_bounds__(FastCfg<EPL>::kMaxWarps * 32, 1)
+__global__ void __launch_bounds__(FastCfg<EPL, KNZ>::kMaxWarps * 32, 1)
 bomp_fast_kernel(const float* __restrict__ alpha, const float* __restrict__ G,
                  int64_t C, int k, int warps_per_cta, int tvecs,
                  int32_t* __restrict__ idx, float* __restrict__ val, int32_t* __restrict__ nsel,
@@ -45,6 +45,10 @@ bomp_fast_kernel(const float* __restrict__ alpha, const float* __restrict__ G,
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     float* tv = smem_t + (size_t)warp * tvecs * K;            // tvecs = max(k-2, 0) vectors of K floats
+    // Cholesky rows: registers for k <= 5; per-warp shared memory for the k <= 10 instantiation, where
+    // 45 extra live scalars per lane cost more (occupancy, spills) than a few broadcast LDS
+    constexpr bool kLInSmem = (KNZ > 5);
+    float* Ls = smem_t + (size_t)warps_per_cta * tvecs * K + (size_t)warp * KNZ * KNZ;
     const int lane_off = 4 * lane;
     const int64_t warp_global = (int64_t)blockIdx.x * warps_per_cta + warp;
     const int64_t n_warps = (int64_t)gridDim.x * warps_per_cta;
@@ -64,7 +68,10 @@ bomp_fast_kernel(const float* __restrict__ alpha, const float* __restrict__ G,
                 a[4 * v] = x.x; a[4 * v + 1] = x.y; a[4 * v + 2] = x.z; a[4 * v + 3] = x.w;
             }
         }
-        float L[KNZ][KNZ];      // L[j][m] = w_m of step j (m < j); diagonal kept as d / 1/d
+        float Lr[kLInSmem ? 1 : KNZ][kLInSmem ? 1 : KNZ];      // L[j][m] = w_m of step j (m < j)
+        auto Lget = [&](int r, int c2) -> float { if constexpr (kLInSmem) return Ls[r * KNZ + c2]; else return Lr[r][c2]; };
+        auto Lset = [&](int r, int c2, float v2) { if constexpr (kLInSmem) { if (lane == 0) Ls[r * KNZ + c2] = v2; } else Lr[r][c2] = v2; };
+        float wrow[KNZ];        // the Cholesky row of the current step (always in registers)
         float dinv[KNZ], y[KNZ];
         int sel[KNZ];
         int cnt = 0;
@@ -109,10 +116,11 @@ bomp_fast_kernel(const float* __restrict__ alpha, const float* __restrict__ G,
                     } else {
                         float s = __ldg(G + (int64_t)sel[m] * K + pick);                 // :327
 #pragma unroll
-                        for (int c = 0; c < KNZ; ++c) if (c < m) s = fmaf(-L[m][c], L[j][c], s);   // :342
+                        for (int c = 0; c < KNZ; ++c) if (c < m) s = fmaf(-Lget(m, c), wrow[c], s);   // :342
                         wm = s * dinv[m];
                     }
-                    L[j][m] = wm;
+                    wrow[m] = wm;
+                    Lset(j, m, wm);
                     ww = fmaf(wm, wm, ww);
                 }
             }
@@ -128,33 +136,49 @@ bomp_fast_kernel(const float* __restrict__ alpha, const float* __restrict__ G,
             // ---- t_j = G[:,pick] - sum_m (w_m/d_m) t_m ; alpha -= (y_j/d_j) t_j
             float cm[KNZ];
 #pragma unroll
-            for (int m = 0; m < KNZ; ++m) if (m < j) cm[m] = L[j][m] * dinv[m];
+            for (int m = 0; m < KNZ; ++m) if (m < j) cm[m] = wrow[m] * dinv[m];
             const float coef = y[j] * di;
+            // m-outer / v-inner in half-row batches: the LDS of one t_m chunk batch are independent and
+            // the FMA chains of the NV/2 chunks interleave (the v-outer order serialised on LDS latency:
+            // ncu showed short-scoreboard + wait as the top stalls of the k = 10 instantiation)
+            constexpr int HB = (NV >= 2) ? NV / 2 : 1;
 #pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                float4 t = g[v];
+            for (int v0 = 0; v0 < NV; v0 += HB) {
 #pragma unroll
                 for (int m = 0; m < KNZ; ++m) {
                     if (m < j) {       // m < j <= k-2  =>  m <= k-3 < tvecs: always stored
-                        const float4 q = *reinterpret_cast<const float4*>(tv + m * K + 128 * v + lane_off);
-                        t.x = fmaf(-cm[m], q.x, t.x); t.y = fmaf(-cm[m], q.y, t.y);
-                        t.z = fmaf(-cm[m], q.z, t.z); t.w = fmaf(-cm[m], q.w, t.w);
+                        float4 q[HB];
+#pragma unroll
+                        for (int h = 0; h < HB; ++h)
+                            q[h] = *reinterpret_cast<const float4*>(tv + m * K + 128 * (v0 + h) + lane_off);
+#pragma unroll
+                        for (int h = 0; h < HB; ++h) {
+                            float4& t = g[v0 + h];
+                            t.x = fmaf(-cm[m], q[h].x, t.x); t.y = fmaf(-cm[m], q[h].y, t.y);
+                            t.z = fmaf(-cm[m], q[h].z, t.z); t.w = fmaf(-cm[m], q[h].w, t.w);
+                        }
                     }
                 }
-                if (j < tvecs) *reinterpret_cast<float4*>(tv + j * K + 128 * v + lane_off) = t;
-                a[4 * v] = fmaf(-coef, t.x, a[4 * v]);         a[4 * v + 1] = fmaf(-coef, t.y, a[4 * v + 1]);
-                a[4 * v + 2] = fmaf(-coef, t.z, a[4 * v + 2]); a[4 * v + 3] = fmaf(-coef, t.w, a[4 * v + 3]);
+#pragma unroll
+                for (int h = 0; h < HB; ++h) {
+                    const int v = v0 + h;
+                    const float4 t = g[v];
+                    if (j < tvecs) *reinterpret_cast<float4*>(tv + j * K + 128 * v + lane_off) = t;
+                    a[4 * v] = fmaf(-coef, t.x, a[4 * v]);         a[4 * v + 1] = fmaf(-coef, t.y, a[4 * v + 1]);
+                    a[4 * v + 2] = fmaf(-coef, t.z, a[4 * v + 2]); a[4 * v + 3] = fmaf(-coef, t.w, a[4 * v + 3]);
+                }
             }
             __syncwarp();      // t_j visible to every lane before the next step's look-ups
         }
         // ---- :354 z = L^-T y
+        if constexpr (kLInSmem) __syncwarp();
         float z[KNZ];
 #pragma unroll
         for (int r = KNZ - 1; r >= 0; --r) {
             if (r < cnt) {
                 float s = y[r];
 #pragma unroll
-                for (int c = KNZ - 1; c > r; --c) if (c < cnt) s = fmaf(-L[c][r], z[c], s);
+                for (int c = KNZ - 1; c > r; --c) if (c < cnt) s = fmaf(-Lget(c, r), z[c], s);
                 z[r] = s * dinv[r];
             } else {
                 z[r] = 0.f;
@@ -187,12 +211,12 @@ int launch_fast(const float* alpha, const float* G, int64_t C, int k,
     constexpr int K = EPL * 32;
     const int tvecs = k > 2 ? k - 2 : 0;
     const size_t per_warp = (size_t)tvecs * K * sizeof(float);
-    int warps = FastCfg<EPL>::kMaxWarps;
+    int warps = FastCfg<EPL, KNZ>::kMaxWarps;
     const size_t budget = 220 * 1024;
-    if (per_warp > 0) warps = (int)std::min<size_t>((size_t)warps, budget / per_warp);
+    if (per_warp > 0) warps = (int)std::min<size_t>((size_t)warps, budget / (per_warp + (KNZ > 5 ? KNZ * KNZ * 4 : 0)));
     if (warps < 1) { set_error("bomp_fast: k=%d K=%d needs more shared memory than one SM has", k, K); return LYS_EUNSUPPORTED; }
     // registers: 64K / (warps*32); the kernel is compiled for <= 128 regs at 512 threads
-    const size_t smem = per_warp * warps;
+    const size_t smem = per_warp * warps + (KNZ > 5 ? (size_t)warps * KNZ * KNZ * sizeof(float) : 0);
     auto kern = bomp_fast_kernel<EPL, KNZ>;
     LYS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks = std::min<int64_t>((C + warps - 1) / warps, (int64_t)sm_count());

@@ -86,6 +86,57 @@ sgemm_kernel(const float* __restrict__ A, int64_t sai, int64_t sap,
     }
 }
 
+// small-tile variant for skinny problems (few output rows, e.g. D*A with n = 128 rows): 32x32
+// tiles keep all SMs busy where the 128x128 kernel would launch a handful of CTAs
+constexpr int SB = 32, SBK = 32;
+
+__global__ void __launch_bounds__(NT)
+sgemm_small_kernel(const float* __restrict__ A, int64_t sai, int64_t sap,
+                   const float* __restrict__ B, int64_t sbp, int64_t sbj,
+                   float* __restrict__ C, int64_t sci, int64_t scj,
+                   int64_t M, int64_t Nc, int Kd)
+{
+    __shared__ float As[SBK][SB + 1];
+    __shared__ float Bs[SBK][SB + 1];
+    const int t = threadIdx.x;
+    const int64_t i0 = (int64_t)blockIdx.y * SB, j0 = (int64_t)blockIdx.x * SB;
+    const int ty = t / 16, tx = t % 16;            // each thread: rows {ty, ty+16}, cols {tx, tx+16}
+    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    const bool a_p_contig = (sap == 1), b_j_contig = (sbj == 1);
+    for (int p0 = 0; p0 < Kd; p0 += SBK) {
+#pragma unroll
+        for (int e = 0; e < (SB * SBK) / NT; ++e) {
+            const int id = t + e * NT;
+            int i, p;
+            if (a_p_contig) { i = id / SBK; p = id % SBK; } else { i = id % SB; p = id / SB; }
+            const int64_t gi = i0 + i; const int gp = p0 + p;
+            As[p][i] = (gi < M && gp < Kd) ? A[gi * sai + gp * sap] : 0.f;
+            int j, q;
+            if (b_j_contig) { j = id % SB; q = id / SB; } else { q = id % SBK; j = id / SBK; }
+            const int64_t gj = j0 + j; const int gq = p0 + q;
+            Bs[q][j] = (gj < Nc && gq < Kd) ? B[gq * sbp + gj * sbj] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < SBK; ++p) {
+            const float a0 = As[p][ty], a1 = As[p][ty + 16], b0 = Bs[p][tx], b1 = Bs[p][tx + 16];
+            acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+            acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const int64_t gi = i0 + ty + 16 * a;
+        if (gi >= M) continue;
+#pragma unroll
+        for (int bq = 0; bq < 2; ++bq) {
+            const int64_t gj = j0 + tx + 16 * bq;
+            if (gj < Nc) C[gi * sci + gj * scj] = acc[a][bq];
+        }
+    }
+}
+
 }  // namespace
 
 int sgemm_strided(const float* A, int64_t sai, int64_t sap,
@@ -94,6 +145,13 @@ int sgemm_strided(const float* A, int64_t sai, int64_t sap,
                   int64_t M, int64_t Nc, int Kd, cudaStream_t stream)
 {
     if (M <= 0 || Nc <= 0) return LYS_OK;
+    const int64_t big_ctas = ((Nc + BN - 1) / BN) * ((M + BM - 1) / BM);
+    if (big_ctas < sm_count() && (Nc + SB - 1) / SB <= 65535 && (M + SB - 1) / SB <= 65535) {
+        dim3 g((unsigned)((Nc + SB - 1) / SB), (unsigned)((M + SB - 1) / SB));
+        sgemm_small_kernel<<<g, NT, 0, stream>>>(A, sai, sap, B, sbp, sbj, C, sci, scj, M, Nc, Kd);
+        LYS_LAUNCH_CHECK("sgemm_small_kernel");
+        return LYS_OK;
+    }
     dim3 grid((unsigned)((Nc + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
     if (grid.y > 65535u) { set_error("sgemm: M too large for one launch"); return LYS_EINVAL; }
     sgemm_kernel<<<grid, NT, 0, stream>>>(A, sai, sap, B, sbp, sbj, C, sci, scj, M, Nc, Kd);

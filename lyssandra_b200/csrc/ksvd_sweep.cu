@@ -68,8 +68,43 @@ __global__ void sweep_bounds_kernel(const int32_t* __restrict__ rowptr, const in
     bounds[id] = lo;
 }
 
-constexpr int SW_WARPS = 32;
-constexpr int SW_U = 8;          // users per warp whose residual rows stay in registers between the phases
+// entry id -> signal index: ent / k by multiply-shift (k <= 32, ent < 2^31; M = ceil(2^(32+s)/k) is exact
+// for every 32-bit numerator because M*k - 2^(32+s) < k <= 2^s)
+struct FastDiv { unsigned long long M; int s; };
+__device__ __forceinline__ int fdiv(int ent, FastDiv d)
+{
+    return (int)(((unsigned long long)(unsigned)ent * d.M) >> (32 + d.s));
+}
+
+constexpr int SW_WARPS = 16;
+constexpr int SW_U = 12;         // users per warp whose ids/coefficients/rows stay in registers (192 per CTA)
+
+// ids of this warp's users of one atom (issued a whole atom ahead) ...
+__device__ __forceinline__ void load_user_ids(const int32_t* __restrict__ entries, int lo, int hi, int warp,
+                                              int (&ent)[SW_U])
+{
+#pragma unroll
+    for (int u = 0; u < SW_U; ++u) {
+        const int p = lo + warp + u * SW_WARPS;
+        ent[u] = (p < hi) ? __ldg(entries + p) : -1;
+    }
+}
+// ... and their coefficients + an L2 prefetch of their residual rows.  Safe while the previous atom
+// is still in flight: an atom's coefficients are only written by that atom's own phase 2, and the
+// rows are only PREFETCHED here (they are re-read after the previous atom's phase 2).
+__device__ __forceinline__ void load_user_coefs(const float* val, const float* R, int lane, int n, FastDiv k,
+                                                const int (&ent)[SW_U], float (&x)[SW_U])
+{
+#pragma unroll
+    for (int u = 0; u < SW_U; ++u) {
+        x[u] = 0.f;
+        if (ent[u] >= 0) {
+            x[u] = val[ent[u]];
+            const char* row = reinterpret_cast<const char*>(R + (int64_t)fdiv(ent[u], k) * n);
+            if (lane * 128 < n * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + lane * 128));
+        }
+    }
+}
 
 template <int NPL>
 __global__ void __launch_bounds__(SW_WARPS * 32, 1)
@@ -79,13 +114,13 @@ ksvd_sweep_kernel(float* __restrict__ R, float* __restrict__ Dt, float* __restri
                   int n, int K, int k, int n_cycles,
                   int32_t* __restrict__ unused,
                   float* __restrict__ partial /* [2][grid][n+1] */, unsigned* __restrict__ flags /* [2][grid] */,
-                  PeerComm pc, unsigned comm_seq0)
+                  PeerComm pc, unsigned comm_seq0, FastDiv kdiv)
 {
     extern __shared__ float sm[];
     float* d_old = sm;                       // [n]
     float* d_new = d_old + n;                // [n]
     float* svec = d_new + n;                 // [n + 2]
-    float* red = svec + (n + 2);             // [SW_WARPS][n + 1]
+    float* red = svec + (n + 2);             // [max(SW_WARPS, groups)][n + 1]
     __shared__ float s_g;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int ldr = n + 1;
@@ -94,44 +129,51 @@ ksvd_sweep_kernel(float* __restrict__ R, float* __restrict__ Dt, float* __restri
     unsigned seq = 0;
 
     for (int cyc = 0; cyc < n_cycles; ++cyc) {
+        // Software pipeline over atoms: the ids/coefficients of atom c+1's users and this CTA's CSR
+        // bounds of atom c+2 are loaded while atom c is in flight, so no dependent address chain
+        // (bounds -> ids -> coefficients -> rows) sits on the per-atom critical path.  Every atom runs
+        // the same protocol; an atom nobody uses (ksvd.py:112-115) is detected from the summed user
+        // count and only skips the refresh (rare, so the wasted sync does not matter).
+        int ent[SW_U]; float x[SW_U];
+        int lo = bounds[b], hi = bounds[b + 1];
+        int lo2 = 0, hi2 = 0;
+        if (K > 1) { lo2 = bounds[(G + 1) + b]; hi2 = bounds[(G + 1) + b + 1]; }
+        load_user_ids(entries, lo, hi, warp, ent);
+        load_user_coefs(val, R, lane, n, kdiv, ent, x);
+
         for (int c = 0; c < K; ++c) {
             const int local_count = rowptr[c + 1] - rowptr[c];
-            if (pc.world == 1 && local_count == 0) {         // ksvd.py:112-115
-                if (b == 0 && t == 0) unused[c] = 1;
-                // the one-thread store above diverges warp 0; without an explicit reconvergence the
-                // `continue` let its lanes reach the next bar.sync separately (found by
-                // compute-sanitizer racecheck: barrier phases slipped after every unused atom)
-                __syncwarp();
-                continue;
-            }
             ++seq;
             const int par = seq & 1;
-            const int lo = bounds[c * (G + 1) + b], hi = bounds[c * (G + 1) + b + 1];
-            for (int f = t; f < n; f += blockDim.x) d_old[f] = Dt[(int64_t)c * n + f];
-
-            // ---- phase 1: this CTA's users; ids, coefficients and rows as one batch of independent loads
-            int ent[SW_U]; float x[SW_U]; float rv[SW_U][NPL];
-            float acc[NPL];
-#pragma unroll
-            for (int q = 0; q < NPL; ++q) acc[q] = 0.f;
-            float sxx = 0.f;
+            // ---- rows of this CTA's users: issued first (L2 hits after the prefetch)
+            float rv[SW_U][NPL];
 #pragma unroll
             for (int u = 0; u < SW_U; ++u) {
-                const int p = lo + warp + u * SW_WARPS;
-                ent[u] = (p < hi) ? entries[p] : -1;
-            }
-#pragma unroll
-            for (int u = 0; u < SW_U; ++u) {
-                x[u] = 0.f;
 #pragma unroll
                 for (int q = 0; q < NPL; ++q) rv[u][q] = 0.f;
                 if (ent[u] >= 0) {
-                    x[u] = val[ent[u]];
-                    const float* r = R + (int64_t)(ent[u] / k) * n;
+                    const float* r = R + (int64_t)fdiv(ent[u], kdiv) * n;
 #pragma unroll
                     for (int q = 0; q < NPL; ++q) { const int f = lane + 32 * q; if (f < n) rv[u][q] = r[f]; }
                 }
             }
+            for (int f = t; f < n; f += blockDim.x) d_old[f] = Dt[(int64_t)c * n + f];
+            // ---- next atom's user ids (its bounds are already in registers), bounds of atom c+2
+            int ent2[SW_U]; float x2n[SW_U];
+            if (c + 1 < K) {
+                load_user_ids(entries, lo2, hi2, warp, ent2);
+            } else {
+#pragma unroll
+                for (int u = 0; u < SW_U; ++u) ent2[u] = -1;
+            }
+            int lo3 = 0, hi3 = 0;
+            if (c + 2 < K) { lo3 = bounds[(c + 2) * (G + 1) + b]; hi3 = bounds[(c + 2) * (G + 1) + b + 1]; }
+
+            // ---- phase 1: partial s = sum_i R[i,:] x_i, sxx = sum x_i^2         (ksvd.py:116-118)
+            float acc[NPL];
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) acc[q] = 0.f;
+            float sxx = 0.f;
 #pragma unroll
             for (int u = 0; u < SW_U; ++u) {
 #pragma unroll
@@ -140,11 +182,11 @@ ksvd_sweep_kernel(float* __restrict__ R, float* __restrict__ Dt, float* __restri
             }
             for (int p = lo + warp + SW_U * SW_WARPS; p < hi; p += SW_WARPS) {       // overflow users (rare)
                 const int e2 = entries[p];
-                const float x2 = val[e2];
-                const float* r = R + (int64_t)(e2 / k) * n;
+                const float xo = val[e2];
+                const float* r = R + (int64_t)fdiv(e2, kdiv) * n;
 #pragma unroll
-                for (int q = 0; q < NPL; ++q) { const int f = lane + 32 * q; if (f < n) acc[q] = fmaf(r[f], x2, acc[q]); }
-                sxx = fmaf(x2, x2, sxx);
+                for (int q = 0; q < NPL; ++q) { const int f = lane + 32 * q; if (f < n) acc[q] = fmaf(r[f], xo, acc[q]); }
+                sxx = fmaf(xo, xo, sxx);
             }
 #pragma unroll
             for (int q = 0; q < NPL; ++q) { const int f = lane + 32 * q; if (f < n) red[warp * ldr + f] = acc[q]; }
@@ -158,13 +200,24 @@ ksvd_sweep_kernel(float* __restrict__ R, float* __restrict__ Dt, float* __restri
             }
             __syncthreads();
             if (t == 0) { __threadfence(); st_release_gpu(flags + (size_t)par * G + b, seq); }
+
+            // ---- overlap with the grid converging: coefficients + row prefetch of the next atom
+            load_user_coefs(val, R, lane, n, kdiv, ent2, x2n);
+
             // ---- grid-wide: wait for every CTA's partial (flag poll = barrier + data-ready in one)
-            if (t < G) { while (ld_acquire_gpu(flags + (size_t)par * G + t) != seq) { } }
+            for (int tt = t; tt < G; tt += blockDim.x) { while (ld_acquire_gpu(flags + (size_t)par * G + tt) != seq) { } }
             __syncthreads();
             if (t < groups * ldr) {
                 const int f = t % ldr, g = t / ldr;
+                const float* src = partial + (size_t)par * G * ldr + f;
                 double s = 0.0;
-                for (int bb = g; bb < G; bb += groups) s += (double)__ldcg(partial + ((size_t)par * G + bb) * ldr + f);
+                for (int b0 = g; b0 < G; b0 += 24 * groups) {         // up to 24 independent L2 loads in flight
+                    float v[24];
+#pragma unroll
+                    for (int q = 0; q < 24; ++q) { const int bb = b0 + q * groups; v[q] = (bb < G) ? __ldcg(src + (size_t)bb * ldr) : 0.f; }
+#pragma unroll
+                    for (int q = 0; q < 24; ++q) s += (double)v[q];     // fixed order: deterministic
+                }
                 red[g * ldr + f] = (float)s;
             }
             __syncthreads();
@@ -198,88 +251,91 @@ ksvd_sweep_kernel(float* __restrict__ R, float* __restrict__ Dt, float* __restri
                     svec[t] = (float)s;
                 }
                 __syncthreads();
-                if (svec[n + 1] == 0.f) {                     // no user on any rank (uniform decision)
-                    if (b == 0 && t == 0) unused[c] = 1;
-                    __syncthreads();
-                    continue;
-                }
             }
-            // ---- new atom                                                        (ksvd.py:118-119)
-            if (warp == 0) {
-                const float sxx_all = svec[n];
-                float sv[NPL], dsq = 0.f;
-#pragma unroll
-                for (int q = 0; q < NPL; ++q) {
-                    const int f = lane + 32 * q;
-                    sv[q] = (f < n) ? fmaf(d_old[f], sxx_all, svec[f]) : 0.f;     // R_k x = R x + d (x.x)
-                    dsq = fmaf(sv[q], sv[q], dsq);
-                }
-                dsq = warp_sum(dsq);
-                const float inv = 1.f / (sqrtf(dsq) + kRefEps);                    // utils/math.py:61-62
-                float g = 0.f;
-#pragma unroll
-                for (int q = 0; q < NPL; ++q) {
-                    const int f = lane + 32 * q;
-                    if (f < n) {
-                        const float dnv = sv[q] * inv;
-                        d_new[f] = dnv;
-                        g = fmaf(d_old[f], dnv, g);
-                        if (b == 0) Dt[(int64_t)c * n + f] = dnv;
-                    }
-                }
-                g = warp_sum(g);
-                if (lane == 0) s_g = g;
-            }
-            __syncthreads();
-            const float g = s_g;
-            // ---- phase 2: x' = R_k^T d' ; R <- R_k - d' x'                      (ksvd.py:121-123)
-            float dn[NPL], dold[NPL];
-#pragma unroll
-            for (int q = 0; q < NPL; ++q) {
-                const int f = lane + 32 * q;
-                dn[q] = (f < n) ? d_new[f] : 0.f;
-                dold[q] = (f < n) ? d_old[f] : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < SW_U; ++u) {
-                if (ent[u] >= 0) {                               // warp-uniform
-                    float dot = 0.f;
-#pragma unroll
-                    for (int q = 0; q < NPL; ++q) dot = fmaf(rv[u][q], dn[q], dot);
-                    dot = warp_sum(dot);
-                    const float xn = fmaf(x[u], g, dot);
-                    float* r = R + (int64_t)(ent[u] / k) * n;
+            const bool atom_used = svec[n + 1] != 0.f;            // uniform over CTAs and ranks
+            if (!atom_used && b == 0 && t == 0) unused[c] = 1;
+            __syncwarp();      // reconverge warp 0 before the next bar.sync (racecheck finding)
+            if (atom_used) {
+                // ---- new atom                                                    (ksvd.py:118-119)
+                if (warp == 0) {
+                    const float sxx_all = svec[n];
+                    float sv[NPL], dsq = 0.f;
 #pragma unroll
                     for (int q = 0; q < NPL; ++q) {
                         const int f = lane + 32 * q;
-                        if (f < n) r[f] = fmaf(-dn[q], xn, fmaf(dold[q], x[u], rv[u][q]));
+                        sv[q] = (f < n) ? fmaf(d_old[f], sxx_all, svec[f]) : 0.f;     // R_k x = R x + d (x.x)
+                        dsq = fmaf(sv[q], sv[q], dsq);
                     }
-                    if (lane == 0) val[ent[u]] = xn;
+                    dsq = warp_sum(dsq);
+                    const float inv = 1.f / (sqrtf(dsq) + kRefEps);                    // utils/math.py:61-62
+                    float g = 0.f;
+#pragma unroll
+                    for (int q = 0; q < NPL; ++q) {
+                        const int f = lane + 32 * q;
+                        if (f < n) {
+                            const float dnv = sv[q] * inv;
+                            d_new[f] = dnv;
+                            g = fmaf(d_old[f], dnv, g);
+                            if (b == 0) Dt[(int64_t)c * n + f] = dnv;
+                        }
+                    }
+                    g = warp_sum(g);
+                    if (lane == 0) s_g = g;
                 }
-            }
-            for (int p = lo + warp + SW_U * SW_WARPS; p < hi; p += SW_WARPS) {
-                const int e2 = entries[p];
-                const float x2 = val[e2];
-                float* r = R + (int64_t)(e2 / k) * n;
-                float r2[NPL], dot = 0.f;
+                __syncthreads();
+                const float g = s_g;
+                // ---- phase 2: x' = R_k^T d' ; R <- R_k - d' x'                  (ksvd.py:121-123)
+                float dn[NPL], dold[NPL];
 #pragma unroll
                 for (int q = 0; q < NPL; ++q) {
                     const int f = lane + 32 * q;
-                    r2[q] = (f < n) ? r[f] : 0.f;
-                    dot = fmaf(r2[q], dn[q], dot);
+                    dn[q] = (f < n) ? d_new[f] : 0.f;
+                    dold[q] = (f < n) ? d_old[f] : 0.f;
                 }
-                dot = warp_sum(dot);
-                const float xn = fmaf(x2, g, dot);
 #pragma unroll
-                for (int q = 0; q < NPL; ++q) {
-                    const int f = lane + 32 * q;
-                    if (f < n) r[f] = fmaf(-dn[q], xn, fmaf(dold[q], x2, r2[q]));
+                for (int u = 0; u < SW_U; ++u) {
+                    if (ent[u] >= 0) {                               // warp-uniform
+                        float dot = 0.f;
+#pragma unroll
+                        for (int q = 0; q < NPL; ++q) dot = fmaf(rv[u][q], dn[q], dot);
+                        dot = warp_sum(dot);
+                        const float xn = fmaf(x[u], g, dot);
+                        float* r = R + (int64_t)fdiv(ent[u], kdiv) * n;
+#pragma unroll
+                        for (int q = 0; q < NPL; ++q) {
+                            const int f = lane + 32 * q;
+                            if (f < n) r[f] = fmaf(-dn[q], xn, fmaf(dold[q], x[u], rv[u][q]));
+                        }
+                        if (lane == 0) val[ent[u]] = xn;
+                    }
                 }
-                __syncwarp();
-                if (lane == 0) val[e2] = xn;
+                for (int p = lo + warp + SW_U * SW_WARPS; p < hi; p += SW_WARPS) {
+                    const int e2 = entries[p];
+                    const float xo = val[e2];
+                    float* r = R + (int64_t)fdiv(e2, kdiv) * n;
+                    float r2[NPL], dot = 0.f;
+#pragma unroll
+                    for (int q = 0; q < NPL; ++q) {
+                        const int f = lane + 32 * q;
+                        r2[q] = (f < n) ? r[f] : 0.f;
+                        dot = fmaf(r2[q], dn[q], dot);
+                    }
+                    dot = warp_sum(dot);
+                    const float xn = fmaf(xo, g, dot);
+#pragma unroll
+                    for (int q = 0; q < NPL; ++q) {
+                        const int f = lane + 32 * q;
+                        if (f < n) r[f] = fmaf(-dn[q], xn, fmaf(dold[q], xo, r2[q]));
+                    }
+                    __syncwarp();
+                    if (lane == 0) val[e2] = xn;
+                }
             }
             // rows/coefficients of this CTA's signals are re-read by other warps of THIS CTA only
             __syncthreads();
+            lo = lo2; hi = hi2; lo2 = lo3; hi2 = hi3;
+#pragma unroll
+            for (int u = 0; u < SW_U; ++u) { ent[u] = ent2[u]; x[u] = x2n[u]; }
         }
     }
 }
@@ -289,13 +345,18 @@ int launch_sweep(float* R, float* Dt, float* val, const int32_t* rowptr, const i
                  int n, int K, int k, int n_cycles, int32_t* unused, float* partial, unsigned* flags,
                  PeerComm pc, unsigned comm_seq0, int grid, cudaStream_t stream)
 {
+    FastDiv kdiv;
+    kdiv.s = 0;
+    while ((1 << kdiv.s) < k) ++kdiv.s;
+    kdiv.M = ((1ull << (32 + kdiv.s)) + (unsigned long long)k - 1) / (unsigned long long)k;
     auto kern = ksvd_sweep_kernel<NPL>;
-    size_t smem = sizeof(float) * (size_t)(2 * n + (n + 2) + SW_WARPS * (n + 1));
+    const int red_rows = std::max(SW_WARPS, (SW_WARPS * 32) / (n + 1));
+    size_t smem = sizeof(float) * (size_t)(2 * n + (n + 2) + red_rows * (n + 1));
     LYS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     LYS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SW_WARPS * 32, smem));
     if (per_sm < 1) { set_error("ksvd sweep kernel does not fit on an SM"); return LYS_ECUDA; }
-    void* args[] = {&R, &Dt, &val, &rowptr, &entries, &bounds, &n, &K, &k, &n_cycles, &unused, &partial, &flags, &pc, &comm_seq0};
+    void* args[] = {&R, &Dt, &val, &rowptr, &entries, &bounds, &n, &K, &k, &n_cycles, &unused, &partial, &flags, &pc, &comm_seq0, &kdiv};
     LYS_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(SW_WARPS * 32), args, smem, stream));
     return LYS_OK;
 }
