@@ -78,20 +78,41 @@ bomp_fast_kernel(const float* __restrict__ alpha, const float* __restrict__ G,
 #pragma unroll
         for (int j = 0; j < KNZ; ++j) {
             if (j >= k) break;
-            // ---- :322 argmax |alpha|, first maximum: in-lane scan in ascending atom order
-            float bval = a[0];
-            int bpos = 0;
+            // ---- :322 argmax |alpha|, FIRST maximum (np.argmax).  Two levels instead of a compare/select
+            // scan (3 ALU ops per element made the ALU pipe the busiest unit, 58 % in ncu):
+            //   1. max of every group of 4 consecutive atoms and of the lane (3-input FMNMX3 tree),
+            //      warp maximum by redux.sync on the bit pattern (|x| >= 0 orders like an integer);
+            //   2. lowest group v holding the maximum in each lane, lowest (v, lane) over the warp by
+            //      redux.sync.min  ==  lowest atom index block, since index = 128 v + 4 lane + c;
+            //   3. warp-uniform switch on v: the owner lane finds the first of its 4 atoms that equals
+            //      the maximum.  Exact ties therefore resolve to the lowest atom index, as in the reference.
+            float gm[NV];
 #pragma unroll
-            for (int r = 1; r < EPL; ++r) {
-                const bool gt = fabsf(a[r]) > fabsf(bval);
-                bval = gt ? a[r] : bval;
-                bpos = gt ? r : bpos;
+            for (int v = 0; v < NV; ++v)
+                gm[v] = fmaxf(fmaxf(fabsf(a[4 * v]), fabsf(a[4 * v + 1])), fmaxf(fabsf(a[4 * v + 2]), fabsf(a[4 * v + 3])));
+            float lmax = gm[0];
+#pragma unroll
+            for (int v = 1; v < NV; ++v) lmax = fmaxf(lmax, gm[v]);
+            const unsigned gbits = __reduce_max_sync(0xffffffffu, __float_as_uint(lmax));
+            const float gmax = __uint_as_float(gbits);
+            int vsel = NV;
+#pragma unroll
+            for (int v = NV - 1; v >= 0; --v) vsel = (gm[v] == gmax) ? v : vsel;
+            const unsigned kmin = __reduce_min_sync(0xffffffffu, vsel < NV ? (unsigned)(vsel * 32 + lane) : 0x7fffffffu);
+            const int vstar = (kmin == 0x7fffffffu) ? 0 : (int)(kmin >> 5);      // no hit only if alpha holds NaNs
+            const int lstar = (kmin == 0x7fffffffu) ? 0 : (int)(kmin & 31u);
+            float e0 = a[0], e1 = a[1], e2 = a[2], e3 = a[3];
+            switch (vstar) {
+#define LYS_CASE(V) case V: if (V < NV) { e0 = a[4 * (V < NV ? V : 0)]; e1 = a[4 * (V < NV ? V : 0) + 1]; e2 = a[4 * (V < NV ? V : 0) + 2]; e3 = a[4 * (V < NV ? V : 0) + 3]; } break;
+                LYS_CASE(1) LYS_CASE(2) LYS_CASE(3) LYS_CASE(4) LYS_CASE(5) LYS_CASE(6) LYS_CASE(7)
+                LYS_CASE(8) LYS_CASE(9) LYS_CASE(10) LYS_CASE(11) LYS_CASE(12) LYS_CASE(13) LYS_CASE(14) LYS_CASE(15)
+#undef LYS_CASE
+                default: break;
             }
-            const int bidx = 128 * (bpos >> 2) + lane_off + (bpos & 3);
-            const unsigned mbits = __float_as_uint(fabsf(bval));
-            const unsigned gbits = __reduce_max_sync(0xffffffffu, mbits);
-            const int pick = (int)__reduce_min_sync(0xffffffffu, mbits == gbits ? (unsigned)bidx : 0x7fffffffu);
-            const float apick = __shfl_sync(0xffffffffu, bval, (pick & 127) >> 2);   // alpha_{j-1}[pick], signed
+            const int cmine = (fabsf(e0) == gmax) ? 0 : (fabsf(e1) == gmax) ? 1 : (fabsf(e2) == gmax) ? 2 : 3;
+            const float vmine = (cmine == 0) ? e0 : (cmine == 1) ? e1 : (cmine == 2) ? e2 : e3;
+            const int pick = 128 * vstar + 4 * lstar + __shfl_sync(0xffffffffu, cmine, lstar);
+            const float apick = __shfl_sync(0xffffffffu, vmine, lstar);          // alpha_{j-1}[pick], signed
             // issue the Gram-row gather NOW (address is always valid): its L2 latency overlaps the
             // scalar Cholesky work below instead of following it
             float4 g[NV];
