@@ -1,18 +1,565 @@
-// bomp_fused.cu — fused correlation + greedy Batch-OMP kernel for the benchmark shapes.
-// (placeholder until the tcgen05 path lands: every shape is reported unsupported so that
-// lys_bomp_encode takes the generic path.)
+// bomp_fused.cu — fused Batch-OMP for n <= 64, K in {256,...,1024}: correlations on the 5th-generation
+// tensor cores, greedy selection straight out of TMEM, one thread per signal.  Alpha never
+// touches HBM and no Gram row is gathered.
+//
+// Replaces sparse_encoder('bomp') (lyssa/sparse_coding.py:629-635,:708-726) and batch_omp
+// (:302-367) for these shapes.  Algebra (same selections and coefficients as the reference):
+// batch_omp keeps alpha_j = alpha0 - G[:,I] z_j (:359); with G = D^T D this is D^T r_j for the
+// residual r_j = x - D_I z_j, so every greedy step is ONE correlation GEMM of the residual tile
+// against the whole dictionary:
+//     step j:  alpha_j = D^T r_j                      tcgen05.mma, fp32-faithful (below)
+//              pick    = first argmax |alpha_j|       (:322; scanned from TMEM, thread = signal)
+//              stop if pick already selected          (:323-325)
+//              w = L^-1 G[I,pick], pivot = 1 - w.w    (:327,:342-344; stop if pivot < eps :335,:345)
+//              L <- [L; w, sqrt(pivot)]               (:337,:348-349)
+//              z = L^-T L^-1 alpha0[I]                (:353-354; alpha0[I] = D_I^T x in fp32)
+//              r_{j+1} = x - D_I z
+// Precision: every fp32 operand is scaled by a power of two and split exactly into two fp16
+// planes (hi = rn16(v), lo = rn16(v - hi), 22+ mantissa bits); hi*hi + lo*hi + hi*lo are
+// accumulated in fp32 in TMEM (3 MMAs per k-step; the dropped lo*lo term is 2^-22 relative).
+//
+// Decomposition: a tile is 128 signals (TMEM lanes = MMA M); atoms are processed in chunks of
+// 256 (MMA N = one 256-column accumulator stage; two stages).  The fp16 planes of the whole
+// dictionary must stay in shared memory: 256 B per atom, i.e. 128 KB for 512 atoms.  For
+// K > 512 two CTAs of a cluster (one TPC) pair up: tcgen05.mma.cta_group::2 with M = 256
+// (128 signals per CTA) reads half of every 256-atom chunk from each CTA's shared memory.
+// Every CTA interleaves TWO tiles ("slots") so that the tensor pipe works on one tile while the
+// other one is scanned / updated.  Roles (288 threads):
+//     warps 0-3  slot 0: thread = signal; TMEM scan, Cholesky, residual, fp16 planes of r
+//     warps 4-7  slot 1: same
+//     warp  8    TMEM allocation; one thread of the pair's leader CTA issues every MMA
+// Barriers: a_ready[slot] (planes of r written; 4 warps per CTA arrive at the leader CTA),
+// acc_full[slot][chunk] (tcgen05.commit, multicast to both CTAs), acc_empty[slot][chunk] (4 warps
+// per CTA arrive at the leader after their last tcgen05.ld of that accumulator).  One barrier
+// per (slot, chunk) — not per TMEM stage — so that every waiter sees EVERY phase of the barrier
+// it waits on (the two slots alternate on the two stages; a parity wait must never be two
+// phases behind).
+//
+// Roofline: tensor pipe.  Per signal k * 2*64*K*3 fp16 flop (1.97 MFLOP at K=1024, k=5) and
+// 4n + 4K bytes of HBM traffic (x in, dense Z row out).
 #include "common.cuh"
+#include "tc_ptx.cuh"
+#include <cuda_fp16.h>
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 namespace lys {
 
-size_t bomp_fused_workspace_bytes(int, int, int64_t, int) { return 0; }
-int bomp_fused_launch_count(int, int, int64_t, int) { return 0; }
+bool profile_begin(cudaStream_t st, const char* name, cudaEvent_t* stop_out);
 
-int bomp_encode_fused(const float*, int64_t, int64_t, const float*, int64_t, const float*,
-                      int, int, int64_t, int, int32_t*, float*, int32_t*, float*, int64_t, int64_t,
-                      void*, size_t, cudaStream_t)
+namespace {
+
+using namespace tc;
+
+constexpr int TM = 128;                  // signals per tile
+constexpr int CH = 256;                  // atoms per MMA chunk / TMEM stage
+constexpr int NF = 64;                   // feature extent of the MMA (n <= 64, zero padded)
+constexpr int NSLOT = 2;                 // interleaved tiles per CTA
+constexpr int A_PLANE = TM * NF * 2;     // 16 KB: one fp16 plane of a residual tile
+constexpr int A_SLOT = 2 * A_PLANE;      // hi + lo
+constexpr int SMEM_A = NSLOT * A_SLOT;   // 64 KB
+constexpr int SMEM_BAR = 256;
+constexpr int THREADS = 288;
+constexpr float kDictScale = 32.f;       // atoms (unit norm) are stored as 32*d: fp16 lo plane stays normal
+
+template <int PAIR> struct Geo {
+    static constexpr int ROWS_B = CH / PAIR;            // atoms of one chunk held by one CTA
+    static constexpr int B_PLANE = ROWS_B * NF * 2;     // bytes of one fp16 plane of one chunk in one CTA
+    static constexpr int B_CHUNK = 2 * B_PLANE;
+    static constexpr int MAX_NCH = 2 * PAIR;            // 128 KB of planes per CTA
+};
+
+// kind::f16 instruction descriptor: D = F32, A = B = F16, both K-major
+template <int PAIR> __host__ __device__ constexpr uint32_t make_idesc()
 {
-    return LYS_EUNSUPPORTED;
+    return (1u << 4) | ((uint32_t)(CH >> 3) << 17) | ((uint32_t)((TM * PAIR) >> 4) << 24);
+}
+
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+__device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+
+// one 32-column piece of a signal's correlations: exact maximum of |v| and the FIRST column
+// attaining it (np.argmax order).  Pass 2 runs on the FMA pipe: e = |v| - m is 0 exactly where
+// the maximum sits and <= -ulp elsewhere, so key = e * (-1e30) + column is the column itself
+// or something huge; the minimum key is the first such column.
+__device__ __forceinline__ void scan32(const uint32_t (&r)[32], int base, float& run_max, int& run_idx)
+{
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fabsf(__uint_as_float(r[i]));
+    float t[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) t[i] = max3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+    t[10] = fmaxf(v[30], v[31]);
+    const float m = max3(max3(t[0], t[1], t[2]), max3(t[3], t[4], t[5]),
+                         max3(max3(t[6], t[7], t[8]), t[9], t[10]));
+    float key[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) key[i] = fmaf(v[i] - m, -1.0e30f, (float)i);
+    float u[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) u[i] = min3(key[3 * i], key[3 * i + 1], key[3 * i + 2]);
+    u[10] = fminf(key[30], key[31]);
+    const float kmin = min3(min3(u[0], u[1], u[2]), min3(u[3], u[4], u[5]),
+                            min3(min3(u[6], u[7], u[8]), u[9], u[10]));
+    if (m > run_max) { run_max = m; run_idx = base + (int)kmin; }       // strict: first maximum wins
+}
+
+// scale r by a power of two so that max|r| lands in [16,32), split into fp16 hi/lo planes and
+// store row `row` of the slot's A operand (canonical K-major no-swizzle layout: 16-byte chunk
+// kc of row r at kc*(TM*16) + r*16)
+__device__ __forceinline__ void store_planes(unsigned char* slotA, int row, const float (&r)[NF])
+{
+    float t[22];
+#pragma unroll
+    for (int i = 0; i < 21; ++i) t[i] = max3(fabsf(r[3 * i]), fabsf(r[3 * i + 1]), fabsf(r[3 * i + 2]));
+    t[21] = fabsf(r[63]);
+    float amax = t[21];
+#pragma unroll
+    for (int i = 0; i < 21; i += 3) amax = fmaxf(amax, max3(t[i], t[i + 1], t[i + 2]));
+    int es = 258 - (int)(__float_as_uint(amax) >> 23);
+    es = min(max(es, 1), 254);
+    const float s = __uint_as_float((uint32_t)es << 23);
+#pragma unroll
+    for (int kc = 0; kc < NF / 8; ++kc) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float a = r[kc * 8 + 2 * e] * s, b = r[kc * 8 + 2 * e + 1] * s;
+            const __half2 h = __floats2half2_rn(a, b);
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+            hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+            lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        *reinterpret_cast<uint4*>(slotA + kc * (TM * 16) + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(slotA + A_PLANE + kc * (TM * 16) + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+template <int KNZ> struct SigState {
+    float x[NF];
+    float L[KNZ][KNZ];          // L[j][m], m < j: Cholesky row of step j (unit diagonal of G assumed, quirk Q1)
+    float dinv[KNZ], y[KNZ];
+    int sel[KNZ];
+    int cnt;
+    bool done;
+};
+
+// everything that follows the argmax of step J for one signal (:323-359)
+template <int J, int KNZ>
+__device__ __forceinline__ void update_step(SigState<KNZ>& st, int pick, bool last,
+                                            const float* __restrict__ Dt, const float* __restrict__ G, int K,
+                                            unsigned char* slotA, int row)
+{
+    bool dup = false;
+#pragma unroll
+    for (int m = 0; m < J; ++m) dup |= (st.sel[m] == pick);
+    if (dup) { st.done = true; return; }                                 // :323-325
+    float g[J > 0 ? J : 1];
+#pragma unroll
+    for (int m = 0; m < J; ++m) g[m] = __ldg(G + (int64_t)st.sel[m] * K + pick);      // :327
+    // alpha0[pick] = d_pick . x
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+    {
+        const float4* dp = reinterpret_cast<const float4*>(Dt + (int64_t)pick * NF);
+#pragma unroll
+        for (int q = 0; q < NF / 4; ++q) {
+            const float4 d = __ldg(dp + q);
+            p0 = fmaf(d.x, st.x[4 * q], p0); p1 = fmaf(d.y, st.x[4 * q + 1], p1);
+            p2 = fmaf(d.z, st.x[4 * q + 2], p2); p3 = fmaf(d.w, st.x[4 * q + 3], p3);
+        }
+    }
+    const float a0 = (p0 + p1) + (p2 + p3);
+    float w[J > 0 ? J : 1];
+    float ww = 0.f;
+#pragma unroll
+    for (int m = 0; m < J; ++m) {                                         // :342 forward substitution
+        float s = g[m];
+#pragma unroll
+        for (int c = 0; c < m; ++c) s = fmaf(-st.L[m][c], w[c], s);
+        w[m] = s * st.dinv[m];
+        ww = fmaf(w[m], w[m], ww);
+    }
+    const float pivot = 1.f - ww;                                         // :334 / :344
+    if (J > 0 && pivot < kPivotEps) { st.done = true; return; }           // :335 / :345
+    const float di = (J == 0) ? 1.f : 1.f / sqrtf(pivot);
+#pragma unroll
+    for (int m = 0; m < J; ++m) st.L[J][m] = w[m];
+    st.dinv[J] = di;
+    {
+        float s = a0;
+#pragma unroll
+        for (int m = 0; m < J; ++m) s = fmaf(-w[m], st.y[m], s);
+        st.y[J] = s * di;
+    }
+    st.sel[J] = pick;
+    st.cnt = J + 1;
+    if (last) return;
+    // z = L^-T y (:354), then the residual of the next step
+    float z[J + 1];
+#pragma unroll
+    for (int r = J; r >= 0; --r) {
+        float s = st.y[r];
+#pragma unroll
+        for (int c = J; c > r; --c) s = fmaf(-st.L[c][r], z[c], s);
+        z[r] = s * st.dinv[r];
+    }
+    float rr[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) rr[f] = st.x[f];
+#pragma unroll
+    for (int m = 0; m <= J; ++m) {
+        const float4* ap = reinterpret_cast<const float4*>(Dt + (int64_t)st.sel[m] * NF);
+        const float zm = -z[m];
+#pragma unroll
+        for (int q = 0; q < NF / 4; ++q) {
+            const float4 d = __ldg(ap + q);
+            rr[4 * q] = fmaf(zm, d.x, rr[4 * q]);         rr[4 * q + 1] = fmaf(zm, d.y, rr[4 * q + 1]);
+            rr[4 * q + 2] = fmaf(zm, d.z, rr[4 * q + 2]); rr[4 * q + 3] = fmaf(zm, d.w, rr[4 * q + 3]);
+        }
+    }
+    store_planes(slotA, row, rr);
+}
+
+template <int KNZ, int PAIR>
+__global__ void __launch_bounds__(THREADS, 1)
+bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
+               const uint4* __restrict__ planes, const float* __restrict__ Dt, const float* __restrict__ G,
+               int K, int nch, int64_t N, int k, int n_units /* clusters */, int rounds,
+               int32_t* __restrict__ idx, float* __restrict__ val, int32_t* __restrict__ nsel,
+               float* __restrict__ Z, int64_t zss)
+{
+    using GE = Geo<PAIR>;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* sB = smem;
+    unsigned char* sA = smem + (size_t)nch * GE::B_CHUNK;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + SMEM_A);
+    // bars[0..1] a_ready[slot], [2 + 4 slot + chunk] acc_full, [10 + 4 slot + chunk] acc_empty; then the TMEM base
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = (PAIR == 2) ? cluster_ctarank() : 0u;
+    const int unit = (PAIR == 2) ? (int)cluster_id_x() : (int)blockIdx.x;
+    const int64_t n_tiles = (N + TM - 1) / TM;
+
+    if (tid == 0) {
+        mbar_init(smem_u32(&bars[0]), 4 * PAIR); mbar_init(smem_u32(&bars[1]), 4 * PAIR);
+        for (int b = 0; b < 8; ++b) { mbar_init(smem_u32(&bars[2 + b]), 1); mbar_init(smem_u32(&bars[10 + b]), 4 * PAIR); }
+        mbar_init_fence();
+    }
+    if (warp == 8) tmem_alloc<PAIR>(smem_u32(tmem_slot), 512);
+    {   // this CTA's share of the dictionary planes: resident for the whole kernel
+        const int items = nch * GE::B_CHUNK / 16;
+        const uint4* src = planes + (size_t)rank * items;
+        uint4* dst = reinterpret_cast<uint4*>(sB);
+        for (int it = tid; it < items; it += THREADS) dst[it] = __ldg(src + it);
+    }
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    if (PAIR == 2) cluster_sync();
+    fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // barrier addresses: waits are local, arrivals of a_ready / acc_empty go to the leader CTA
+    const uint32_t bar_local = smem_u32(&bars[0]);
+    const uint32_t bar_lead = mapa(bar_local, 0);
+
+    if (warp == 8) {
+        // ------------------------------------------------------------------- MMA issuer
+        if (rank == 0 && lane == 0) {
+            const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+            constexpr uint32_t LBO_A = TM * 16, LBO_B = GE::ROWS_B * 16, SBO = 128;
+            constexpr uint32_t kIdesc = make_idesc<PAIR>();
+            // small products first: (lo,hi) (hi,lo) (hi,hi)
+            const int pa[3] = {1, 0, 0};
+            const int pb[3] = {0, 1, 0};
+            uint32_t u = 0;
+            uint32_t prev_bar[2] = {0u, 0u}, prev_par[2] = {0u, 0u};      // who used each TMEM stage last
+            for (int r = 0; r < rounds; ++r) {
+                for (int j = 0; j < k; ++j) {
+                    const uint32_t q = (uint32_t)(r * k + j);
+#pragma unroll 1
+                    for (int s = 0; s < NSLOT; ++s) {
+                        mbar_wait(bar_local + 8 * s, q & 1);                         // planes of r_j landed (both CTAs)
+                        fence_after();
+#pragma unroll 1
+                        for (int c = 0; c < nch; ++c, ++u) {
+                            const uint32_t stg = u & 1;
+                            if (u >= 2) {                                              // stage drained (both CTAs)
+                                mbar_wait(prev_bar[stg], prev_par[stg]);
+                                fence_after();
+                            }
+                            prev_bar[stg] = bar_local + 8 * (10 + 4 * s + c);
+                            prev_par[stg] = q & 1;
+                            const uint32_t d_tmem = tmem_base + stg * CH;
+                            uint32_t acc = 0;
+#pragma unroll
+                            for (int p = 0; p < 3; ++p) {
+#pragma unroll
+                                for (int ks = 0; ks < NF / 16; ++ks) {
+                                    const uint64_t ad = make_desc(a_base + s * A_SLOT + pa[p] * A_PLANE + ks * 2 * LBO_A, LBO_A, SBO);
+                                    const uint64_t bd = make_desc(b_base + (c * 2 + pb[p]) * GE::B_PLANE + ks * 2 * LBO_B, LBO_B, SBO);
+                                    mma_f16<PAIR>(d_tmem, ad, bd, kIdesc, acc);
+                                    acc = 1;
+                                }
+                            }
+                            commit<PAIR>(bar_local + 8 * (2 + 4 * s + c));            // accumulator ready
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------- one thread = one signal
+        const int s = warp >> 2;                      // slot
+        const int quad = warp & 3;                    // TMEM lane quadrant of this warp
+        const int row = quad * 32 + lane;             // row of the tile
+        unsigned char* slotA = sA + s * A_SLOT;
+        const uint32_t tq = tmem_base + ((uint32_t)(quad * 32) << 16);
+        SigState<KNZ> st;
+        for (int r = 0; r < rounds; ++r) {
+            const int64_t tile = (((int64_t)r * n_units + unit) * PAIR + rank) * NSLOT + s;
+            const int64_t sig = tile * TM + row;
+            const bool live = (tile < n_tiles) && (sig < N);
+            // ---- load x, publish its planes (:631 alpha0 = D^T x is step 0 of the loop)
+            if (live) {
+                const float* xp = X + sig * xss;
+                if (xfs == 1 && n == NF && ((reinterpret_cast<uintptr_t>(xp) & 15) == 0)) {
+#pragma unroll
+                    for (int q = 0; q < NF / 4; ++q) {
+                        const float4 v4 = __ldg(reinterpret_cast<const float4*>(xp) + q);
+                        st.x[4 * q] = v4.x; st.x[4 * q + 1] = v4.y; st.x[4 * q + 2] = v4.z; st.x[4 * q + 3] = v4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) st.x[f] = (f < n) ? __ldg(xp + (int64_t)f * xfs) : 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int f = 0; f < NF; ++f) st.x[f] = 0.f;
+            }
+            store_planes(slotA, row, st.x);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * s);
+            st.cnt = 0;
+            st.done = !live;
+            // ---- dense rows of this warp's 32 signals: zero fill now (the tensor pipe is busy with
+            // step 0), the k coefficients are scattered after the last step (:308,:365)
+            if (Z) {
+                const int64_t sig0 = tile * TM + quad * 32;
+                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int rr = 0; rr < 32; ++rr) {
+                    if (tile >= n_tiles || sig0 + rr >= N) break;
+                    float* zrow = Z + (sig0 + rr) * zss;
+                    for (int c4 = lane * 4; c4 < K; c4 += 128) *reinterpret_cast<float4*>(zrow + c4) = zero;
+                }
+                __syncwarp();
+            }
+            for (int j = 0; j < k; ++j) {
+                // ---- :322 argmax |alpha_j| over all atoms, first maximum
+                float run_max = -1.f;
+                int run_idx = 0;
+                const uint32_t u0 = (uint32_t)(((r * k + j) * NSLOT + s) * nch);
+#pragma unroll 1
+                for (int c = 0; c < nch; ++c) {
+                    const uint32_t u = u0 + c, stg = u & 1;
+                    mbar_wait(bar_local + 8 * (2 + 4 * s + c), (uint32_t)(r * k + j) & 1);
+                    fence_after();
+                    const uint32_t ta = tq + stg * CH;
+                    uint32_t b0[32], b1[32];
+                    LYS_TMEM_LD_X32(ta, b0);
+#pragma unroll
+                    for (int sc = 0; sc < CH / 32; sc += 2) {
+                        LYS_TMEM_WAIT_X32(b0);
+                        LYS_TMEM_LD_X32(ta + (sc + 1) * 32, b1);
+                        scan32(b0, c * CH + sc * 32, run_max, run_idx);
+                        LYS_TMEM_WAIT_X32(b1);
+                        if (sc + 2 < CH / 32) LYS_TMEM_LD_X32(ta + (sc + 2) * 32, b0);
+                        else {
+                            // every tcgen05.ld of this stage has completed: hand it back to the MMA issuer
+                            fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * (10 + 4 * s + c));
+                        }
+                        scan32(b1, c * CH + (sc + 1) * 32, run_max, run_idx);
+                    }
+                }
+                const bool last = (j + 1 >= k);
+                if (!st.done) {
+                    switch (j) {
+#define LYS_STEP(JJ) case JJ: if constexpr (JJ < KNZ) update_step<JJ, KNZ>(st, run_idx, last, Dt, G, K, slotA, row); break;
+                        LYS_STEP(0) LYS_STEP(1) LYS_STEP(2) LYS_STEP(3) LYS_STEP(4)
+                        LYS_STEP(5) LYS_STEP(6) LYS_STEP(7) LYS_STEP(8) LYS_STEP(9)
+#undef LYS_STEP
+                        default: break;
+                    }
+                }
+                if (!last) {
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * s);
+                }
+            }
+            // ---- :354 z = L^-T y, outputs
+            if (live) {
+                float z[KNZ];
+#pragma unroll
+                for (int rr = KNZ - 1; rr >= 0; --rr) {
+                    if (rr < st.cnt) {
+                        float sacc = st.y[rr];
+#pragma unroll
+                        for (int c = KNZ - 1; c > rr; --c) if (c < st.cnt) sacc = fmaf(-st.L[c][rr], z[c], sacc);
+                        z[rr] = sacc * st.dinv[rr];
+                    } else {
+                        z[rr] = 0.f;
+                    }
+                }
+#pragma unroll
+                for (int m = 0; m < KNZ; ++m) {
+                    if (m < k) {
+                        const bool has = m < st.cnt;
+                        idx[sig * k + m] = has ? st.sel[m] : -1;
+                        val[sig * k + m] = has ? z[m] : 0.f;
+                        if (Z && has) Z[sig * zss + st.sel[m]] = z[m];
+                    }
+                }
+                if (nsel) nsel[sig] = st.cnt;
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (PAIR == 2) cluster_sync();
+    if (warp == 8) {
+        fence_after();
+        tmem_dealloc<PAIR>(tmem_base, 512);
+    }
+}
+
+// D (n <= 64, K) fp32 -> (a) the scaled fp16 hi/lo planes in the kernel's shared-memory layout,
+// per CTA of the pair: [rank][chunk][plane][k-chunk][row] 16-byte items; (b) Dt (K, 64) fp32
+// atom-major, zero padded, for the residual / alpha0 gathers.
+template <int PAIR>
+__global__ void prep_dict_kernel(const float* __restrict__ D, int64_t ldd, int n, int K, int nch,
+                                 unsigned char* __restrict__ planes, float* __restrict__ Dt)
+{
+    using GE = Geo<PAIR>;
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;        // one 16-byte chunk of one atom
+    if (item >= K * (NF / 8)) return;
+    const int atom = item % K, kc = item / K;
+    const int c = atom / CH, nn = atom % CH, h = nn / GE::ROWS_B, row = nn % GE::ROWS_B;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int f = kc * 8 + e;
+        v[e] = (f < n) ? __ldg(D + (int64_t)f * ldd + atom) : 0.f;
+        Dt[(int64_t)atom * NF + f] = v[e];
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float a = v[2 * e] * kDictScale, b = v[2 * e + 1] * kDictScale;
+        const __half2 hh = __floats2half2_rn(a, b);
+        const float2 hf = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
+        hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
+        lo[e] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    unsigned char* base = planes + (size_t)h * nch * GE::B_CHUNK + (size_t)c * GE::B_CHUNK + kc * (GE::ROWS_B * 16) + row * 16;
+    *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(base + GE::B_PLANE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+bool fused_shape_ok(int n, int K, int k)
+{
+    if (const char* e = getenv("LYS_BOMP_PATH")) if (!strcmp(e, "legacy")) return false;
+    return n >= 1 && n <= NF && K >= CH && (K % CH) == 0 && K <= 4 * CH && k >= 1 && k <= 10;
+}
+
+size_t planes_bytes(int K) { return (size_t)K * NF * 2 * 2; }      // hi + lo fp16 of every atom
+size_t dt_bytes(int K) { return (size_t)K * NF * sizeof(float); }
+
+template <int KNZ, int PAIR>
+int launch_tc(const float* X, int64_t xfs, int64_t xss, int n, const void* planes, const float* Dt, const float* G,
+              int K, int64_t N, int k, int32_t* idx, float* val, int32_t* nsel, float* Z, int64_t zss,
+              cudaStream_t stream)
+{
+    using GE = Geo<PAIR>;
+    const int nch = K / CH;
+    const size_t smem = (size_t)nch * GE::B_CHUNK + SMEM_A + SMEM_BAR;
+    auto kern = bomp_tc_kernel<KNZ, PAIR>;
+    LYS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t n_tiles = (N + TM - 1) / TM;
+    const int64_t tiles_per_unit = (int64_t)PAIR * NSLOT;
+    int units = sm_count() / PAIR;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    cfg.blockDim = dim3(THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    if (PAIR == 2) {
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cfg.gridDim = dim3((unsigned)(2 * units), 1, 1);
+        int max_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) == cudaSuccess && max_clusters > 0)
+            units = std::min(units, max_clusters);
+        else
+            (void)cudaGetLastError();
+    }
+    units = (int)std::max<int64_t>(1, std::min<int64_t>(units, (n_tiles + tiles_per_unit - 1) / tiles_per_unit));
+    const int rounds = (int)((n_tiles + (int64_t)units * tiles_per_unit - 1) / ((int64_t)units * tiles_per_unit));
+    cfg.gridDim = dim3((unsigned)(units * PAIR), 1, 1);
+    LYS_CUDA(cudaLaunchKernelEx(&cfg, kern, X, xfs, xss, n, reinterpret_cast<const uint4*>(planes), Dt, G, K, nch, N, k,
+                                units, rounds, idx, val, nsel, Z, zss));
+    LYS_LAUNCH_CHECK("bomp_tc_kernel");
+    return LYS_OK;
+}
+
+}  // namespace
+
+size_t bomp_fused_workspace_bytes(int n, int K, int64_t, int k)
+{
+    if (!fused_shape_ok(n, K, k)) return 0;
+    return align_up(planes_bytes(K), 256) + align_up(dt_bytes(K), 256) + 256;
+}
+
+int bomp_fused_launch_count(int n, int K, int64_t, int k) { return fused_shape_ok(n, K, k) ? 2 : 0; }
+
+// returns LYS_EUNSUPPORTED for shapes this path is not built for (the caller then takes the
+// two-kernel path); Z must be signal-major (atom stride 1) here, other layouts are filled by the caller
+int bomp_encode_fused(const float* X, int64_t xfs, int64_t xss, const float* D, int64_t ldd, const float* G,
+                      int n, int K, int64_t N, int k, int32_t* idx, float* val, int32_t* nsel,
+                      float* Z, int64_t zas, int64_t zss, void* workspace, size_t workspace_bytes, cudaStream_t stream)
+{
+    if (!fused_shape_ok(n, K, k)) return LYS_EUNSUPPORTED;
+    if (Z && (zas != 1 || (zss % 4) != 0 || (reinterpret_cast<uintptr_t>(Z) & 15) != 0)) return LYS_EUNSUPPORTED;
+    if (workspace_bytes < bomp_fused_workspace_bytes(n, K, N, k)) return LYS_EWORKSPACE;
+    unsigned char* planes = reinterpret_cast<unsigned char*>(workspace);
+    float* Dt = reinterpret_cast<float*>(planes + align_up(planes_bytes(K), 256));
+    const int pair = (K > 2 * CH) ? 2 : 1;
+    const int nch = K / CH;
+    const int items = K * (NF / 8);
+    if (pair == 2) prep_dict_kernel<2><<<(items + 255) / 256, 256, 0, stream>>>(D, ldd, n, K, nch, planes, Dt);
+    else prep_dict_kernel<1><<<(items + 255) / 256, 256, 0, stream>>>(D, ldd, n, K, nch, planes, Dt);
+    LYS_LAUNCH_CHECK("prep_dict_kernel");
+    cudaEvent_t stop_ev;
+    const bool prof = profile_begin(stream, "bomp_tc_kernel", &stop_ev);
+    int rc;
+    if (k <= 5) {
+        rc = (pair == 2) ? launch_tc<5, 2>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, stream)
+                         : launch_tc<5, 1>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, stream);
+    } else {
+        rc = (pair == 2) ? launch_tc<10, 2>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, stream)
+                         : launch_tc<10, 1>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, stream);
+    }
+    if (prof) cudaEventRecord(stop_ev, stream);
+    return rc;
 }
 
 }  // namespace lys
