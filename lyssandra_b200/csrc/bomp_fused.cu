@@ -24,10 +24,11 @@
 // K > 512 two CTAs of a cluster (one TPC) pair up: tcgen05.mma.cta_group::2 with M = 256
 // (128 signals per CTA) reads half of every 256-atom chunk from each CTA's shared memory.
 // Every CTA interleaves TWO tiles ("slots") so that the tensor pipe works on one tile while the
-// other one is scanned / updated.  Roles (288 threads):
-//     warps 0-3  slot 0: thread = signal; TMEM scan, Cholesky, residual, fp16 planes of r
+// other one is scanned / updated.  Roles (384 threads, registers re-balanced with setmaxnreg):
+//     warps 0-3  slot 0: thread = signal; TMEM scan, Cholesky, residual, fp16 planes of r   (232 regs)
 //     warps 4-7  slot 1: same
-//     warp  8    TMEM allocation; one thread of the pair's leader CTA issues every MMA
+//     warp  8    TMEM allocation; one thread of the pair's leader CTA issues every MMA       (40 regs)
+//     warps 9-11 idle (they complete the third warpgroup)
 // Barriers: a_ready[slot] (planes of r written; 4 warps per CTA arrive at the leader CTA),
 // acc_full[slot][chunk] (tcgen05.commit, multicast to both CTAs), acc_empty[slot][chunk] (4 warps
 // per CTA arrive at the leader after their last tcgen05.ld of that accumulator).  One barrier
@@ -60,7 +61,7 @@ constexpr int A_PLANE = TM * NF * 2;     // 16 KB: one fp16 plane of a residual 
 constexpr int A_SLOT = 2 * A_PLANE;      // hi + lo
 constexpr int SMEM_A = NSLOT * A_SLOT;   // 64 KB
 constexpr int SMEM_BAR = 256;
-constexpr int THREADS = 288;
+constexpr int THREADS = 384;               // 2 signal warpgroups + 1 warpgroup that holds the MMA-issuing warp
 constexpr float kDictScale = 32.f;       // atoms (unit norm) are stored as 32*d: fp16 lo plane stays normal
 
 template <int PAIR> struct Geo {
@@ -139,7 +140,7 @@ __device__ __forceinline__ void store_planes(unsigned char* slotA, int row, cons
 }
 
 template <int KNZ> struct SigState {
-    float x[NF];
+    float r[NF];                // residual r_j (r_0 = x)
     float L[KNZ][KNZ];          // L[j][m], m < j: Cholesky row of step j (unit diagonal of G assumed, quirk Q1)
     float dinv[KNZ], y[KNZ];
     int sel[KNZ];
@@ -147,11 +148,16 @@ template <int KNZ> struct SigState {
     bool done;
 };
 
-// everything that follows the argmax of step J for one signal (:323-359)
+// everything that follows the argmax of step J for one signal (:323-359).
+// With u_m the orthonormalised directions of the selected atoms (u_j = (d_pick - sum_m w_m u_m) / L[j][j],
+// w = L^-1 G[I,pick] is the new Cholesky row, :342) the reference's quantities are
+//     y_j = (L^-1 alpha0[I])_j = (d_pick . r_j) / L[j][j]        r_{j+1} = r_j - y_j u_j
+// so a step needs ONE scattered atom gather (d_pick); u_0..u_{k-3} live in a per-CTA scratch
+// laid out [vector][feature][signal] so that a warp's accesses to them are coalesced.
 template <int J, int KNZ>
-__device__ __forceinline__ void update_step(SigState<KNZ>& st, int pick, bool last,
+__device__ __forceinline__ void update_step(SigState<KNZ>& st, int pick, bool last, int k,
                                             const float* __restrict__ Dt, const float* __restrict__ G, int K,
-                                            unsigned char* slotA, int row)
+                                            float* U, unsigned char* slotA, int row)
 {
     bool dup = false;
 #pragma unroll
@@ -160,18 +166,15 @@ __device__ __forceinline__ void update_step(SigState<KNZ>& st, int pick, bool la
     float g[J > 0 ? J : 1];
 #pragma unroll
     for (int m = 0; m < J; ++m) g[m] = __ldg(G + (int64_t)st.sel[m] * K + pick);      // :327
-    // alpha0[pick] = d_pick . x
-    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+    float d[NF];
     {
         const float4* dp = reinterpret_cast<const float4*>(Dt + (int64_t)pick * NF);
 #pragma unroll
         for (int q = 0; q < NF / 4; ++q) {
-            const float4 d = __ldg(dp + q);
-            p0 = fmaf(d.x, st.x[4 * q], p0); p1 = fmaf(d.y, st.x[4 * q + 1], p1);
-            p2 = fmaf(d.z, st.x[4 * q + 2], p2); p3 = fmaf(d.w, st.x[4 * q + 3], p3);
+            const float4 v4 = __ldg(dp + q);
+            d[4 * q] = v4.x; d[4 * q + 1] = v4.y; d[4 * q + 2] = v4.z; d[4 * q + 3] = v4.w;
         }
     }
-    const float a0 = (p0 + p1) + (p2 + p3);
     float w[J > 0 ? J : 1];
     float ww = 0.f;
 #pragma unroll
@@ -185,42 +188,35 @@ __device__ __forceinline__ void update_step(SigState<KNZ>& st, int pick, bool la
     const float pivot = 1.f - ww;                                         // :334 / :344
     if (J > 0 && pivot < kPivotEps) { st.done = true; return; }           // :335 / :345
     const float di = (J == 0) ? 1.f : 1.f / sqrtf(pivot);
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll
+    for (int q = 0; q < NF / 4; ++q) {
+        p0 = fmaf(d[4 * q], st.r[4 * q], p0);         p1 = fmaf(d[4 * q + 1], st.r[4 * q + 1], p1);
+        p2 = fmaf(d[4 * q + 2], st.r[4 * q + 2], p2); p3 = fmaf(d[4 * q + 3], st.r[4 * q + 3], p3);
+    }
+    const float yj = ((p0 + p1) + (p2 + p3)) * di;
 #pragma unroll
     for (int m = 0; m < J; ++m) st.L[J][m] = w[m];
     st.dinv[J] = di;
-    {
-        float s = a0;
-#pragma unroll
-        for (int m = 0; m < J; ++m) s = fmaf(-w[m], st.y[m], s);
-        st.y[J] = s * di;
-    }
+    st.y[J] = yj;
     st.sel[J] = pick;
     st.cnt = J + 1;
     if (last) return;
-    // z = L^-T y (:354), then the residual of the next step
-    float z[J + 1];
 #pragma unroll
-    for (int r = J; r >= 0; --r) {
-        float s = st.y[r];
+    for (int m = 0; m < J; ++m) {
+        const float wm = -w[m];
+        const float* um = U + (size_t)m * NF * TM;
 #pragma unroll
-        for (int c = J; c > r; --c) s = fmaf(-st.L[c][r], z[c], s);
-        z[r] = s * st.dinv[r];
+        for (int f = 0; f < NF; ++f) d[f] = fmaf(wm, __ldcg(um + f * TM), d[f]);
     }
-    float rr[NF];
+    const bool keep = (J + 2 < k);                 // u_J is needed by steps J+1 .. k-2
 #pragma unroll
-    for (int f = 0; f < NF; ++f) rr[f] = st.x[f];
-#pragma unroll
-    for (int m = 0; m <= J; ++m) {
-        const float4* ap = reinterpret_cast<const float4*>(Dt + (int64_t)st.sel[m] * NF);
-        const float zm = -z[m];
-#pragma unroll
-        for (int q = 0; q < NF / 4; ++q) {
-            const float4 d = __ldg(ap + q);
-            rr[4 * q] = fmaf(zm, d.x, rr[4 * q]);         rr[4 * q + 1] = fmaf(zm, d.y, rr[4 * q + 1]);
-            rr[4 * q + 2] = fmaf(zm, d.z, rr[4 * q + 2]); rr[4 * q + 3] = fmaf(zm, d.w, rr[4 * q + 3]);
-        }
+    for (int f = 0; f < NF; ++f) {
+        const float u = d[f] * di;
+        if (keep) __stcg(U + ((size_t)J * NF + f) * TM, u);
+        st.r[f] = fmaf(-yj, u, st.r[f]);
     }
-    store_planes(slotA, row, rr);
+    store_planes(slotA, row, st.r);
 }
 
 template <int KNZ, int PAIR>
@@ -229,7 +225,7 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                const uint4* __restrict__ planes, const float* __restrict__ Dt, const float* __restrict__ G,
                int K, int nch, int64_t N, int k, int n_units /* clusters */, int rounds,
                int32_t* __restrict__ idx, float* __restrict__ val, int32_t* __restrict__ nsel,
-               float* __restrict__ Z, int64_t zss)
+               float* __restrict__ Z, int64_t zss, float* __restrict__ scratch)
 {
     using GE = Geo<PAIR>;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -266,9 +262,11 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
     const uint32_t bar_local = smem_u32(&bars[0]);
     const uint32_t bar_lead = mapa(bar_local, 0);
 
-    if (warp == 8) {
+    if (warp >= 8) {
         // ------------------------------------------------------------------- MMA issuer
-        if (rank == 0 && lane == 0) {
+        // (warps 9-11 only exist so that this warpgroup can hand its registers to the other two)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == 8 && rank == 0 && lane == 0) {
             const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
             constexpr uint32_t LBO_A = TM * 16, LBO_B = GE::ROWS_B * 16, SBO = 128;
             constexpr uint32_t kIdesc = make_idesc<PAIR>();
@@ -314,12 +312,15 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
         __syncwarp();
     } else {
         // ------------------------------------------------------------- one thread = one signal
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
         const int s = warp >> 2;                      // slot
         const int quad = warp & 3;                    // TMEM lane quadrant of this warp
         const int row = quad * 32 + lane;             // row of the tile
         unsigned char* slotA = sA + s * A_SLOT;
         const uint32_t tq = tmem_base + ((uint32_t)(quad * 32) << 16);
         SigState<KNZ> st;
+        const int n_keep = k > 2 ? k - 2 : 0;
+        float* U = scratch + ((size_t)(blockIdx.x * NSLOT + s) * n_keep) * NF * TM + row;
         for (int r = 0; r < rounds; ++r) {
             const int64_t tile = (((int64_t)r * n_units + unit) * PAIR + rank) * NSLOT + s;
             const int64_t sig = tile * TM + row;
@@ -331,17 +332,17 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
 #pragma unroll
                     for (int q = 0; q < NF / 4; ++q) {
                         const float4 v4 = __ldg(reinterpret_cast<const float4*>(xp) + q);
-                        st.x[4 * q] = v4.x; st.x[4 * q + 1] = v4.y; st.x[4 * q + 2] = v4.z; st.x[4 * q + 3] = v4.w;
+                        st.r[4 * q] = v4.x; st.r[4 * q + 1] = v4.y; st.r[4 * q + 2] = v4.z; st.r[4 * q + 3] = v4.w;
                     }
                 } else {
 #pragma unroll
-                    for (int f = 0; f < NF; ++f) st.x[f] = (f < n) ? __ldg(xp + (int64_t)f * xfs) : 0.f;
+                    for (int f = 0; f < NF; ++f) st.r[f] = (f < n) ? __ldg(xp + (int64_t)f * xfs) : 0.f;
                 }
             } else {
 #pragma unroll
-                for (int f = 0; f < NF; ++f) st.x[f] = 0.f;
+                for (int f = 0; f < NF; ++f) st.r[f] = 0.f;
             }
-            store_planes(slotA, row, st.x);
+            store_planes(slotA, row, st.r);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * s);
@@ -391,7 +392,7 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                 const bool last = (j + 1 >= k);
                 if (!st.done) {
                     switch (j) {
-#define LYS_STEP(JJ) case JJ: if constexpr (JJ < KNZ) update_step<JJ, KNZ>(st, run_idx, last, Dt, G, K, slotA, row); break;
+#define LYS_STEP(JJ) case JJ: if constexpr (JJ < KNZ) update_step<JJ, KNZ>(st, run_idx, last, k, Dt, G, K, U, slotA, row); break;
                         LYS_STEP(0) LYS_STEP(1) LYS_STEP(2) LYS_STEP(3) LYS_STEP(4)
                         LYS_STEP(5) LYS_STEP(6) LYS_STEP(7) LYS_STEP(8) LYS_STEP(9)
 #undef LYS_STEP
@@ -482,11 +483,13 @@ bool fused_shape_ok(int n, int K, int k)
 
 size_t planes_bytes(int K) { return (size_t)K * NF * 2 * 2; }      // hi + lo fp16 of every atom
 size_t dt_bytes(int K) { return (size_t)K * NF * sizeof(float); }
+// orthonormalised directions u_0..u_{k-3} of every signal in flight: [CTA][slot][vector][feature][signal]
+size_t scratch_bytes(int k) { return (size_t)sm_count() * NSLOT * (k > 2 ? k - 2 : 0) * NF * TM * sizeof(float); }
 
 template <int KNZ, int PAIR>
 int launch_tc(const float* X, int64_t xfs, int64_t xss, int n, const void* planes, const float* Dt, const float* G,
               int K, int64_t N, int k, int32_t* idx, float* val, int32_t* nsel, float* Z, int64_t zss,
-              cudaStream_t stream)
+              float* scratch, cudaStream_t stream)
 {
     using GE = Geo<PAIR>;
     const int nch = K / CH;
@@ -516,7 +519,7 @@ int launch_tc(const float* X, int64_t xfs, int64_t xss, int n, const void* plane
     const int rounds = (int)((n_tiles + (int64_t)units * tiles_per_unit - 1) / ((int64_t)units * tiles_per_unit));
     cfg.gridDim = dim3((unsigned)(units * PAIR), 1, 1);
     LYS_CUDA(cudaLaunchKernelEx(&cfg, kern, X, xfs, xss, n, reinterpret_cast<const uint4*>(planes), Dt, G, K, nch, N, k,
-                                units, rounds, idx, val, nsel, Z, zss));
+                                units, rounds, idx, val, nsel, Z, zss, scratch));
     LYS_LAUNCH_CHECK("bomp_tc_kernel");
     return LYS_OK;
 }
@@ -526,7 +529,7 @@ int launch_tc(const float* X, int64_t xfs, int64_t xss, int n, const void* plane
 size_t bomp_fused_workspace_bytes(int n, int K, int64_t, int k)
 {
     if (!fused_shape_ok(n, K, k)) return 0;
-    return align_up(planes_bytes(K), 256) + align_up(dt_bytes(K), 256) + 256;
+    return align_up(planes_bytes(K), 256) + align_up(dt_bytes(K), 256) + align_up(scratch_bytes(k), 256) + 256;
 }
 
 int bomp_fused_launch_count(int n, int K, int64_t, int k) { return fused_shape_ok(n, K, k) ? 2 : 0; }
@@ -542,6 +545,7 @@ int bomp_encode_fused(const float* X, int64_t xfs, int64_t xss, const float* D, 
     if (workspace_bytes < bomp_fused_workspace_bytes(n, K, N, k)) return LYS_EWORKSPACE;
     unsigned char* planes = reinterpret_cast<unsigned char*>(workspace);
     float* Dt = reinterpret_cast<float*>(planes + align_up(planes_bytes(K), 256));
+    float* scratch = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Dt) + align_up(dt_bytes(K), 256));
     const int pair = (K > 2 * CH) ? 2 : 1;
     const int nch = K / CH;
     const int items = K * (NF / 8);
@@ -552,11 +556,11 @@ int bomp_encode_fused(const float* X, int64_t xfs, int64_t xss, const float* D, 
     const bool prof = profile_begin(stream, "bomp_tc_kernel", &stop_ev);
     int rc;
     if (k <= 5) {
-        rc = (pair == 2) ? launch_tc<5, 2>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, stream)
-                         : launch_tc<5, 1>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, stream);
+        rc = (pair == 2) ? launch_tc<5, 2>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream)
+                         : launch_tc<5, 1>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream);
     } else {
-        rc = (pair == 2) ? launch_tc<10, 2>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, stream)
-                         : launch_tc<10, 1>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, stream);
+        rc = (pair == 2) ? launch_tc<10, 2>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream)
+                         : launch_tc<10, 1>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream);
     }
     if (prof) cudaEventRecord(stop_ev, stream);
     return rc;
