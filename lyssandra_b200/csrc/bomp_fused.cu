@@ -80,31 +80,47 @@ template <int PAIR> __host__ __device__ constexpr uint32_t make_idesc()
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 __device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
 
-// one 32-column piece of a signal's correlations: exact maximum of |v| and the FIRST column
-// attaining it (np.argmax order).  Pass 2 runs on the FMA pipe: e = |v| - m is 0 exactly where
-// the maximum sits and <= -ulp elsewhere, so key = e * (-1e30) + column is the column itself
-// or something huge; the minimum key is the first such column.
-__device__ __forceinline__ void scan32(const uint32_t (&r)[32], int base, float& run_max, int& run_idx)
+// Argmax of |alpha| over all atoms for one signal, FIRST maximum (np.argmax, :322), in two levels.
+// Level 1, per 32-column piece read from TMEM: exact maximum of |v| with a 3-input max tree; if it
+// beats the running maximum (strictly: earlier pieces win ties) the piece is kept in registers.
+// Level 2, once per step on the kept piece: e = |v| - m is 0 exactly where the maximum sits and
+// <= -ulp elsewhere, so key = e * (-1e30) + column is the column itself or something huge and
+// the minimum key is the first column attaining the maximum.
+struct ArgmaxState {
+    float run_max;
+    int run_piece;
+    uint32_t kept[32];
+};
+
+__device__ __forceinline__ void scan32(const uint32_t (&r)[32], int piece, ArgmaxState& am)
 {
-    float v[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = fabsf(__uint_as_float(r[i]));
     float t[11];
 #pragma unroll
-    for (int i = 0; i < 10; ++i) t[i] = max3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
-    t[10] = fmaxf(v[30], v[31]);
+    for (int i = 0; i < 10; ++i)
+        t[i] = max3(fabsf(__uint_as_float(r[3 * i])), fabsf(__uint_as_float(r[3 * i + 1])), fabsf(__uint_as_float(r[3 * i + 2])));
+    t[10] = fmaxf(fabsf(__uint_as_float(r[30])), fabsf(__uint_as_float(r[31])));
     const float m = max3(max3(t[0], t[1], t[2]), max3(t[3], t[4], t[5]),
                          max3(max3(t[6], t[7], t[8]), t[9], t[10]));
+    if (m > am.run_max) {
+        am.run_max = m;
+        am.run_piece = piece;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) am.kept[i] = r[i];
+    }
+}
+
+__device__ __forceinline__ int argmax_finish(const ArgmaxState& am)
+{
     float key[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) key[i] = fmaf(v[i] - m, -1.0e30f, (float)i);
+    for (int i = 0; i < 32; ++i) key[i] = fmaf(fabsf(__uint_as_float(am.kept[i])) - am.run_max, -1.0e30f, (float)i);
     float u[11];
 #pragma unroll
     for (int i = 0; i < 10; ++i) u[i] = min3(key[3 * i], key[3 * i + 1], key[3 * i + 2]);
     u[10] = fminf(key[30], key[31]);
     const float kmin = min3(min3(u[0], u[1], u[2]), min3(u[3], u[4], u[5]),
                             min3(min3(u[6], u[7], u[8]), u[9], u[10]));
-    if (m > run_max) { run_max = m; run_idx = base + (int)kmin; }       // strict: first maximum wins
+    return am.run_piece * 32 + (int)kmin;
 }
 
 // scale r by a power of two so that max|r| lands in [16,32), split into fp16 hi/lo planes and
@@ -362,8 +378,11 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
             }
             for (int j = 0; j < k; ++j) {
                 // ---- :322 argmax |alpha_j| over all atoms, first maximum
-                float run_max = -1.f;
-                int run_idx = 0;
+                ArgmaxState am;
+                am.run_max = -1.f;
+                am.run_piece = 0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) am.kept[i] = 0u;
                 const uint32_t u0 = (uint32_t)(((r * k + j) * NSLOT + s) * nch);
 #pragma unroll 1
                 for (int c = 0; c < nch; ++c) {
@@ -377,7 +396,7 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                     for (int sc = 0; sc < CH / 32; sc += 2) {
                         LYS_TMEM_WAIT_X32(b0);
                         LYS_TMEM_LD_X32(ta + (sc + 1) * 32, b1);
-                        scan32(b0, c * CH + sc * 32, run_max, run_idx);
+                        scan32(b0, c * (CH / 32) + sc, am);
                         LYS_TMEM_WAIT_X32(b1);
                         if (sc + 2 < CH / 32) LYS_TMEM_LD_X32(ta + (sc + 2) * 32, b0);
                         else {
@@ -386,10 +405,11 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                             __syncwarp();
                             if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * (10 + 4 * s + c));
                         }
-                        scan32(b1, c * CH + (sc + 1) * 32, run_max, run_idx);
+                        scan32(b1, c * (CH / 32) + sc + 1, am);
                     }
                 }
                 const bool last = (j + 1 >= k);
+                const int run_idx = argmax_finish(am);
                 if (!st.done) {
                     switch (j) {
 #define LYS_STEP(JJ) case JJ: if constexpr (JJ < KNZ) update_step<JJ, KNZ>(st, run_idx, last, k, Dt, G, K, U, slotA, row); break;

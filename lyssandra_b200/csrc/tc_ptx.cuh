@@ -38,10 +38,13 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
 __device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-// arrive on a barrier given by its shared::cluster address (own CTA or the pair's leader)
+// arrive on a barrier given by its shared::cluster address (own CTA or the pair's leader).
+// Default semantics (release at CTA scope): what crosses the CTA pair through these barriers is
+// ordered by tcgen05 fences / fence.proxy.async, not by global-memory visibility, and a
+// cluster-scope release costs a MEMBAR.GPU per arrival (measured: 12 % of the warp samples).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
 {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
@@ -49,7 +52,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "{\n\t"
         ".reg .pred P1;\n\t"
         "LAB_WAIT:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
         "@P1 bra DONE;\n\t"
         "bra LAB_WAIT;\n\t"
         "DONE:\n\t"
