@@ -56,12 +56,10 @@ using namespace tc;
 constexpr int TM = 128;                  // signals per tile
 constexpr int CH = 256;                  // atoms per MMA chunk / TMEM stage
 constexpr int NF = 64;                   // feature extent of the MMA (n <= 64, zero padded)
-constexpr int NSLOT = 2;                 // interleaved tiles per CTA
 constexpr int A_PLANE = TM * NF * 2;     // 16 KB: one fp16 plane of a residual tile
 constexpr int A_SLOT = 2 * A_PLANE;      // hi + lo
-constexpr int SMEM_A = NSLOT * A_SLOT;   // 64 KB
 constexpr int SMEM_BAR = 256;
-constexpr int THREADS = 384;               // 2 signal warpgroups + 1 warpgroup that holds the MMA-issuing warp
+constexpr int MAX_SLOTS = 3;
 constexpr float kDictScale = 32.f;       // atoms (unit norm) are stored as 32*d: fp16 lo plane stays normal
 
 template <int PAIR> struct Geo {
@@ -86,41 +84,64 @@ __device__ __forceinline__ float min3(float a, float b, float c) { return fminf(
 // Level 2, once per step on the kept piece: e = |v| - m is 0 exactly where the maximum sits and
 // <= -ulp elsewhere, so key = e * (-1e30) + column is the column itself or something huge and
 // the minimum key is the first column attaining the maximum.
-struct ArgmaxState {
-    float run_max;
-    int run_piece;
-    uint32_t kept[32];
+template <int N> struct Tree3 {           // 3-input reduction trees (FMNMX3)
+    static __device__ __forceinline__ float vmax(const float (&a)[N])
+    {
+        constexpr int M = (N + 2) / 3;
+        float t[M];
+#pragma unroll
+        for (int i = 0; i < N / 3; ++i) t[i] = max3(a[3 * i], a[3 * i + 1], a[3 * i + 2]);
+        if (N % 3 == 1) t[M - 1] = a[N - 1];
+        if (N % 3 == 2) t[M - 1] = fmaxf(a[N - 2], a[N - 1]);
+        return Tree3<M>::vmax(t);
+    }
+    static __device__ __forceinline__ float vmin(const float (&a)[N])
+    {
+        constexpr int M = (N + 2) / 3;
+        float t[M];
+#pragma unroll
+        for (int i = 0; i < N / 3; ++i) t[i] = min3(a[3 * i], a[3 * i + 1], a[3 * i + 2]);
+        if (N % 3 == 1) t[M - 1] = a[N - 1];
+        if (N % 3 == 2) t[M - 1] = fminf(a[N - 2], a[N - 1]);
+        return Tree3<M>::vmin(t);
+    }
+};
+template <> struct Tree3<1> {
+    static __device__ __forceinline__ float vmax(const float (&a)[1]) { return a[0]; }
+    static __device__ __forceinline__ float vmin(const float (&a)[1]) { return a[0]; }
 };
 
-__device__ __forceinline__ void scan32(const uint32_t (&r)[32], int piece, ArgmaxState& am)
+template <int PIECE> struct ArgmaxState {
+    float run_max;
+    int run_piece;
+    uint32_t kept[PIECE];
+};
+
+template <int PIECE>
+__device__ __forceinline__ void scan_piece(const uint32_t (&r)[PIECE], int piece, ArgmaxState<PIECE>& am)
 {
-    float t[11];
+    float v[PIECE];
 #pragma unroll
-    for (int i = 0; i < 10; ++i)
-        t[i] = max3(fabsf(__uint_as_float(r[3 * i])), fabsf(__uint_as_float(r[3 * i + 1])), fabsf(__uint_as_float(r[3 * i + 2])));
-    t[10] = fmaxf(fabsf(__uint_as_float(r[30])), fabsf(__uint_as_float(r[31])));
-    const float m = max3(max3(t[0], t[1], t[2]), max3(t[3], t[4], t[5]),
-                         max3(max3(t[6], t[7], t[8]), t[9], t[10]));
+    for (int i = 0; i < PIECE; ++i) v[i] = fabsf(__uint_as_float(r[i]));
+    const float m = Tree3<PIECE>::vmax(v);
     if (m > am.run_max) {
         am.run_max = m;
         am.run_piece = piece;
+        // keep 2*v (exact): a multiply runs on the full-rate FMA pipe, a MOV would queue behind the
+        // max tree on the half-rate ALU pipe (measured: FMNMX3 2.0, FMUL 0.5-1.0 cycles per warp instruction)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) am.kept[i] = r[i];
+        for (int i = 0; i < PIECE; ++i) am.kept[i] = __float_as_uint(2.0f * __uint_as_float(r[i]));
     }
 }
 
-__device__ __forceinline__ int argmax_finish(const ArgmaxState& am)
+template <int PIECE>
+__device__ __forceinline__ int argmax_finish(const ArgmaxState<PIECE>& am)
 {
-    float key[32];
+    float key[PIECE];
+    const float m2 = 2.0f * am.run_max;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) key[i] = fmaf(fabsf(__uint_as_float(am.kept[i])) - am.run_max, -1.0e30f, (float)i);
-    float u[11];
-#pragma unroll
-    for (int i = 0; i < 10; ++i) u[i] = min3(key[3 * i], key[3 * i + 1], key[3 * i + 2]);
-    u[10] = fminf(key[30], key[31]);
-    const float kmin = min3(min3(u[0], u[1], u[2]), min3(u[3], u[4], u[5]),
-                            min3(min3(u[6], u[7], u[8]), u[9], u[10]));
-    return am.run_piece * 32 + (int)kmin;
+    for (int i = 0; i < PIECE; ++i) key[i] = fmaf(fabsf(__uint_as_float(am.kept[i])) - m2, -1.0e30f, (float)i);
+    return am.run_piece * PIECE + (int)Tree3<PIECE>::vmin(key);
 }
 
 // scale r by a power of two so that max|r| lands in [16,32), split into fp16 hi/lo planes and
@@ -235,8 +256,26 @@ __device__ __forceinline__ void update_step(SigState<KNZ>& st, int pick, bool la
     store_planes(slotA, row, st.r);
 }
 
-template <int KNZ, int PAIR>
-__global__ void __launch_bounds__(THREADS, 1)
+// NS = tiles ("slots") interleaved per CTA: NS signal warpgroups + one warpgroup holding the MMA warp.
+// NS = 3 needs 96 KB of residual planes next to the 128 KB of dictionary planes and leaves 160
+// registers per signal thread; NS = 2 leaves 232 (used for k > 5, whose Cholesky state is larger).
+// bring-up instrumentation (LYS_TC_TIMING=1): cycles per role/phase, summed over warps (lane 0)
+__device__ unsigned long long g_tc_timing[16];
+template <bool ON> struct PhaseTimer {
+    long long t;
+    __device__ __forceinline__ void start() { if (ON) t = clock64(); }
+    __device__ __forceinline__ void lap(int phase, int lane)
+    {
+        if (ON) {
+            const long long now = clock64();
+            if (lane == 0) atomicAdd(&g_tc_timing[phase], (unsigned long long)(now - t));
+            t = now;
+        }
+    }
+};
+
+template <int KNZ, int PAIR, int NS, bool TIMING>
+__global__ void __launch_bounds__((NS + 1) * 128, 1)
 bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                const uint4* __restrict__ planes, const float* __restrict__ Dt, const float* __restrict__ G,
                int K, int nch, int64_t N, int k, int n_units /* clusters */, int rounds,
@@ -244,12 +283,18 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                float* __restrict__ Z, int64_t zss, float* __restrict__ scratch)
 {
     using GE = Geo<PAIR>;
+    constexpr int THREADS = (NS + 1) * 128;
+    constexpr int PIECE = (NS == 3) ? 16 : 32;       // TMEM columns per tcgen05.ld
+    constexpr int NP = CH / PIECE;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sB = smem;
     unsigned char* sA = smem + (size_t)nch * GE::B_CHUNK;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + SMEM_A);
-    // bars[0..1] a_ready[slot], [2 + 4 slot + chunk] acc_full, [10 + 4 slot + chunk] acc_empty; then the TMEM base
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + NS * A_SLOT);
+    // bars[slot] a_ready, [4 + 4 slot + chunk] acc_full, [16 + 4 slot + chunk] acc_empty; then the TMEM base
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+    // block of zeros, source of the bulk (TMA) stores that zero-fill the dense code rows
+    constexpr int ZB = (NS == 3) ? 2048 : 16384;
+    unsigned char* zbuf = reinterpret_cast<unsigned char*>(bars) + SMEM_BAR;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = (PAIR == 2) ? cluster_ctarank() : 0u;
@@ -257,17 +302,18 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
     const int64_t n_tiles = (N + TM - 1) / TM;
 
     if (tid == 0) {
-        mbar_init(smem_u32(&bars[0]), 4 * PAIR); mbar_init(smem_u32(&bars[1]), 4 * PAIR);
-        for (int b = 0; b < 8; ++b) { mbar_init(smem_u32(&bars[2 + b]), 1); mbar_init(smem_u32(&bars[10 + b]), 4 * PAIR); }
+        for (int b = 0; b < NS; ++b) mbar_init(smem_u32(&bars[b]), 4 * PAIR);
+        for (int b = 0; b < 4 * NS; ++b) { mbar_init(smem_u32(&bars[4 + b]), 1); mbar_init(smem_u32(&bars[16 + b]), 4 * PAIR); }
         mbar_init_fence();
     }
-    if (warp == 8) tmem_alloc<PAIR>(smem_u32(tmem_slot), 512);
+    if (warp == 4 * NS) tmem_alloc<PAIR>(smem_u32(tmem_slot), 512);
     {   // this CTA's share of the dictionary planes: resident for the whole kernel
         const int items = nch * GE::B_CHUNK / 16;
         const uint4* src = planes + (size_t)rank * items;
         uint4* dst = reinterpret_cast<uint4*>(sB);
         for (int it = tid; it < items; it += THREADS) dst[it] = __ldg(src + it);
     }
+    for (int it = tid; it < ZB / 16; it += THREADS) reinterpret_cast<uint4*>(zbuf)[it] = make_uint4(0u, 0u, 0u, 0u);
     fence_async_smem();
     fence_before();
     __syncthreads();
@@ -278,48 +324,52 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
     const uint32_t bar_local = smem_u32(&bars[0]);
     const uint32_t bar_lead = mapa(bar_local, 0);
 
-    if (warp >= 8) {
+    if (warp >= 4 * NS) {
         // ------------------------------------------------------------------- MMA issuer
-        // (warps 9-11 only exist so that this warpgroup can hand its registers to the other two)
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (warp == 8 && rank == 0 && lane == 0) {
+        // (the other three warps of this warpgroup only exist so that it can hand its registers over)
+        if constexpr (NS == 3) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == 4 * NS && rank == 0 && lane == 0) {
             const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
             constexpr uint32_t LBO_A = TM * 16, LBO_B = GE::ROWS_B * 16, SBO = 128;
             constexpr uint32_t kIdesc = make_idesc<PAIR>();
-            // small products first: (lo,hi) (hi,lo) (hi,hi)
-            const int pa[3] = {1, 0, 0};
-            const int pb[3] = {0, 1, 0};
             uint32_t u = 0;
-            uint32_t prev_bar[2] = {0u, 0u}, prev_par[2] = {0u, 0u};      // who used each TMEM stage last
+            uint32_t prev_bar0 = 0u, prev_bar1 = 0u, prev_par0 = 0u, prev_par1 = 0u;   // who used each TMEM stage last
+            PhaseTimer<TIMING> pt;
+            pt.start();
             for (int r = 0; r < rounds; ++r) {
                 for (int j = 0; j < k; ++j) {
                     const uint32_t q = (uint32_t)(r * k + j);
 #pragma unroll 1
-                    for (int s = 0; s < NSLOT; ++s) {
+                    for (int s = 0; s < NS; ++s) {
                         mbar_wait(bar_local + 8 * s, q & 1);                         // planes of r_j landed (both CTAs)
                         fence_after();
+                        pt.lap(8, 0);
 #pragma unroll 1
                         for (int c = 0; c < nch; ++c, ++u) {
                             const uint32_t stg = u & 1;
                             if (u >= 2) {                                              // stage drained (both CTAs)
-                                mbar_wait(prev_bar[stg], prev_par[stg]);
+                                mbar_wait(stg ? prev_bar1 : prev_bar0, stg ? prev_par1 : prev_par0);
                                 fence_after();
                             }
-                            prev_bar[stg] = bar_local + 8 * (10 + 4 * s + c);
-                            prev_par[stg] = q & 1;
+                            pt.lap(9, 0);
+                            const uint32_t eb = bar_local + 8 * (16 + 4 * s + c);
+                            if (stg) { prev_bar1 = eb; prev_par1 = q & 1; } else { prev_bar0 = eb; prev_par0 = q & 1; }
                             const uint32_t d_tmem = tmem_base + stg * CH;
-                            uint32_t acc = 0;
+                            const uint32_t a_hi = a_base + s * A_SLOT, a_lo = a_hi + A_PLANE;
+                            const uint32_t b_hi = b_base + (c * 2) * GE::B_PLANE, b_lo = b_hi + GE::B_PLANE;
+                            // small products first: (lo,hi) (hi,lo) (hi,hi)
 #pragma unroll
-                            for (int p = 0; p < 3; ++p) {
+                            for (int ks = 0; ks < NF / 16; ++ks)
+                                mma_f16<PAIR>(d_tmem, make_desc(a_lo + ks * 2 * LBO_A, LBO_A, SBO), make_desc(b_hi + ks * 2 * LBO_B, LBO_B, SBO), kIdesc, ks > 0);
 #pragma unroll
-                                for (int ks = 0; ks < NF / 16; ++ks) {
-                                    const uint64_t ad = make_desc(a_base + s * A_SLOT + pa[p] * A_PLANE + ks * 2 * LBO_A, LBO_A, SBO);
-                                    const uint64_t bd = make_desc(b_base + (c * 2 + pb[p]) * GE::B_PLANE + ks * 2 * LBO_B, LBO_B, SBO);
-                                    mma_f16<PAIR>(d_tmem, ad, bd, kIdesc, acc);
-                                    acc = 1;
-                                }
-                            }
-                            commit<PAIR>(bar_local + 8 * (2 + 4 * s + c));            // accumulator ready
+                            for (int ks = 0; ks < NF / 16; ++ks)
+                                mma_f16<PAIR>(d_tmem, make_desc(a_hi + ks * 2 * LBO_A, LBO_A, SBO), make_desc(b_lo + ks * 2 * LBO_B, LBO_B, SBO), kIdesc, 1);
+#pragma unroll
+                            for (int ks = 0; ks < NF / 16; ++ks)
+                                mma_f16<PAIR>(d_tmem, make_desc(a_hi + ks * 2 * LBO_A, LBO_A, SBO), make_desc(b_hi + ks * 2 * LBO_B, LBO_B, SBO), kIdesc, 1);
+                            commit<PAIR>(bar_local + 8 * (4 + 4 * s + c));            // accumulator ready
+                            pt.lap(10, 0);
                         }
                     }
                 }
@@ -328,7 +378,8 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
         __syncwarp();
     } else {
         // ------------------------------------------------------------- one thread = one signal
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        if constexpr (NS == 3) asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
         const int s = warp >> 2;                      // slot
         const int quad = warp & 3;                    // TMEM lane quadrant of this warp
         const int row = quad * 32 + lane;             // row of the tile
@@ -336,9 +387,11 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
         const uint32_t tq = tmem_base + ((uint32_t)(quad * 32) << 16);
         SigState<KNZ> st;
         const int n_keep = k > 2 ? k - 2 : 0;
-        float* U = scratch + ((size_t)(blockIdx.x * NSLOT + s) * n_keep) * NF * TM + row;
+        float* U = scratch + ((size_t)(blockIdx.x * NS + s) * n_keep) * NF * TM + row;
+        PhaseTimer<TIMING> pt;
+        pt.start();
         for (int r = 0; r < rounds; ++r) {
-            const int64_t tile = (((int64_t)r * n_units + unit) * PAIR + rank) * NSLOT + s;
+            const int64_t tile = (((int64_t)r * n_units + unit) * PAIR + rank) * NS + s;
             const int64_t sig = tile * TM + row;
             const bool live = (tile < n_tiles) && (sig < N);
             // ---- load x, publish its planes (:631 alpha0 = D^T x is step 0 of the loop)
@@ -364,52 +417,88 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
             if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * s);
             st.cnt = 0;
             st.done = !live;
-            // ---- dense rows of this warp's 32 signals: zero fill now (the tensor pipe is busy with
-            // step 0), the k coefficients are scattered after the last step (:308,:365)
-            if (Z) {
-                const int64_t sig0 = tile * TM + quad * 32;
-                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int rr = 0; rr < 32; ++rr) {
-                    if (tile >= n_tiles || sig0 + rr >= N) break;
-                    float* zrow = Z + (sig0 + rr) * zss;
-                    for (int c4 = lane * 4; c4 < K; c4 += 128) *reinterpret_cast<float4*>(zrow + c4) = zero;
-                }
-                __syncwarp();
-            }
+            pt.lap(0, lane);
+            const int64_t sig0 = tile * TM + quad * 32;          // first of this warp's 32 signals
             for (int j = 0; j < k; ++j) {
+                // ---- dense rows (:308): zero fill of this warp's 32 rows by bulk (TMA) stores from the block
+                // of zeros in shared memory, a k-th per step: no LSU traffic, no warp stalls.  The
+                // coefficients are scattered after the last step, once the bulk stores have completed.
+                if (Z && tile < n_tiles && lane == 0 && sig0 < N) {
+                    const int64_t rows = (N - sig0 < 32) ? (N - sig0) : 32;
+                    const bool contiguous = (zss == K);
+                    const int64_t total = rows * K * 4;
+                    const int nseg = contiguous ? (int)((total + ZB - 1) / ZB) : (int)rows * ((K * 4 + ZB - 1) / ZB);
+                    const int per_row = (K * 4 + ZB - 1) / ZB;
+                    const int s1 = (int)(((int64_t)nseg * (j + 1)) / k);
+                    for (int sg = (int)(((int64_t)nseg * j) / k); sg < s1; ++sg) {
+                        char* gp; int64_t bytes;
+                        if (contiguous) {
+                            gp = reinterpret_cast<char*>(Z + sig0 * zss) + (int64_t)sg * ZB;
+                            bytes = (total - (int64_t)sg * ZB < ZB) ? total - (int64_t)sg * ZB : ZB;
+                        } else {
+                            const int rr = sg / per_row, part = sg % per_row;
+                            gp = reinterpret_cast<char*>(Z + (sig0 + rr) * zss) + (int64_t)part * ZB;
+                            bytes = ((int64_t)K * 4 - (int64_t)part * ZB < ZB) ? (int64_t)K * 4 - (int64_t)part * ZB : ZB;
+                        }
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     ::"l"(gp), "r"(smem_u32(zbuf)), "r"((uint32_t)bytes) : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                pt.lap(1, lane);
                 // ---- :322 argmax |alpha_j| over all atoms, first maximum
-                ArgmaxState am;
+                ArgmaxState<PIECE> am;
                 am.run_max = -1.f;
                 am.run_piece = 0;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) am.kept[i] = 0u;
-                const uint32_t u0 = (uint32_t)(((r * k + j) * NSLOT + s) * nch);
+                for (int i = 0; i < PIECE; ++i) am.kept[i] = 0u;
+                const uint32_t u0 = (uint32_t)(((r * k + j) * NS + s) * nch);
 #pragma unroll 1
                 for (int c = 0; c < nch; ++c) {
-                    const uint32_t u = u0 + c, stg = u & 1;
-                    mbar_wait(bar_local + 8 * (2 + 4 * s + c), (uint32_t)(r * k + j) & 1);
+                    const uint32_t stg = (u0 + c) & 1;
+                    mbar_wait(bar_local + 8 * (4 + 4 * s + c), (uint32_t)(r * k + j) & 1);
                     fence_after();
+                    pt.lap(2, lane);
                     const uint32_t ta = tq + stg * CH;
-                    uint32_t b0[32], b1[32];
-                    LYS_TMEM_LD_X32(ta, b0);
+                    uint32_t b0[PIECE], b1[PIECE];
+                    if constexpr (PIECE == 32) {
+                        LYS_TMEM_LD_X32(ta, b0);
 #pragma unroll
-                    for (int sc = 0; sc < CH / 32; sc += 2) {
-                        LYS_TMEM_WAIT_X32(b0);
-                        LYS_TMEM_LD_X32(ta + (sc + 1) * 32, b1);
-                        scan32(b0, c * (CH / 32) + sc, am);
-                        LYS_TMEM_WAIT_X32(b1);
-                        if (sc + 2 < CH / 32) LYS_TMEM_LD_X32(ta + (sc + 2) * 32, b0);
-                        else {
-                            // every tcgen05.ld of this stage has completed: hand it back to the MMA issuer
-                            fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * (10 + 4 * s + c));
+                        for (int sc = 0; sc < NP; sc += 2) {
+                            LYS_TMEM_WAIT_X32(b0);
+                            LYS_TMEM_LD_X32(ta + (sc + 1) * PIECE, b1);
+                            scan_piece<PIECE>(b0, c * NP + sc, am);
+                            LYS_TMEM_WAIT_X32(b1);
+                            if (sc + 2 < NP) LYS_TMEM_LD_X32(ta + (sc + 2) * PIECE, b0);
+                            else {
+                                // every tcgen05.ld of this stage has completed: hand it back to the MMA issuer
+                                fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * (16 + 4 * s + c));
+                            }
+                            scan_piece<PIECE>(b1, c * NP + sc + 1, am);
                         }
-                        scan32(b1, c * (CH / 32) + sc + 1, am);
+                    } else {
+                        LYS_TMEM_LD_X16(ta, b0);
+#pragma unroll
+                        for (int sc = 0; sc < NP; sc += 2) {
+                            LYS_TMEM_WAIT_X16(b0);
+                            LYS_TMEM_LD_X16(ta + (sc + 1) * PIECE, b1);
+                            scan_piece<PIECE>(b0, c * NP + sc, am);
+                            LYS_TMEM_WAIT_X16(b1);
+                            if (sc + 2 < NP) LYS_TMEM_LD_X16(ta + (sc + 2) * PIECE, b0);
+                            else {
+                                fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * (16 + 4 * s + c));
+                            }
+                            scan_piece<PIECE>(b1, c * NP + sc + 1, am);
+                        }
                     }
+                    pt.lap(3, lane);
                 }
                 const bool last = (j + 1 >= k);
-                const int run_idx = argmax_finish(am);
+                const int run_idx = argmax_finish<PIECE>(am);
                 if (!st.done) {
                     switch (j) {
 #define LYS_STEP(JJ) case JJ: if constexpr (JJ < KNZ) update_step<JJ, KNZ>(st, run_idx, last, k, Dt, G, K, U, slotA, row); break;
@@ -424,8 +513,11 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * s);
                 }
+                pt.lap(4, lane);
             }
             // ---- :354 z = L^-T y, outputs
+            if (Z && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            __syncwarp();                   // this warp's zero fill is complete before any lane scatters
             if (live) {
                 float z[KNZ];
 #pragma unroll
@@ -450,12 +542,13 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                 }
                 if (nsel) nsel[sig] = st.cnt;
             }
+            pt.lap(5, lane);
         }
     }
     fence_before();
     __syncthreads();
     if (PAIR == 2) cluster_sync();
-    if (warp == 8) {
+    if (warp == 4 * NS) {
         fence_after();
         tmem_dealloc<PAIR>(tmem_base, 512);
     }
@@ -504,20 +597,22 @@ bool fused_shape_ok(int n, int K, int k)
 size_t planes_bytes(int K) { return (size_t)K * NF * 2 * 2; }      // hi + lo fp16 of every atom
 size_t dt_bytes(int K) { return (size_t)K * NF * sizeof(float); }
 // orthonormalised directions u_0..u_{k-3} of every signal in flight: [CTA][slot][vector][feature][signal]
-size_t scratch_bytes(int k) { return (size_t)sm_count() * NSLOT * (k > 2 ? k - 2 : 0) * NF * TM * sizeof(float); }
+size_t scratch_bytes(int k) { return (size_t)sm_count() * MAX_SLOTS * (k > 2 ? k - 2 : 0) * NF * TM * sizeof(float); }
 
-template <int KNZ, int PAIR>
+template <int KNZ, int PAIR, int NS>
 int launch_tc(const float* X, int64_t xfs, int64_t xss, int n, const void* planes, const float* Dt, const float* G,
               int K, int64_t N, int k, int32_t* idx, float* val, int32_t* nsel, float* Z, int64_t zss,
               float* scratch, cudaStream_t stream)
 {
     using GE = Geo<PAIR>;
     const int nch = K / CH;
-    const size_t smem = (size_t)nch * GE::B_CHUNK + SMEM_A + SMEM_BAR;
-    auto kern = bomp_tc_kernel<KNZ, PAIR>;
+    constexpr int THREADS = (NS + 1) * 128;
+    const size_t smem = (size_t)nch * GE::B_CHUNK + (size_t)NS * A_SLOT + SMEM_BAR + (NS == 3 ? 2048 : 16384);
+    static const bool timing = getenv("LYS_TC_TIMING") != nullptr;
+    auto kern = timing ? bomp_tc_kernel<KNZ, PAIR, NS, true> : bomp_tc_kernel<KNZ, PAIR, NS, false>;
     LYS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n_tiles = (N + TM - 1) / TM;
-    const int64_t tiles_per_unit = (int64_t)PAIR * NSLOT;
+    const int64_t tiles_per_unit = (int64_t)PAIR * NS;
     int units = sm_count() / PAIR;
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
@@ -575,15 +670,30 @@ int bomp_encode_fused(const float* X, int64_t xfs, int64_t xss, const float* D, 
     cudaEvent_t stop_ev;
     const bool prof = profile_begin(stream, "bomp_tc_kernel", &stop_ev);
     int rc;
-    if (k <= 5) {
-        rc = (pair == 2) ? launch_tc<5, 2>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream)
-                         : launch_tc<5, 1>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream);
+    static const int slots = getenv("LYS_TC_SLOTS") ? atoi(getenv("LYS_TC_SLOTS")) : 2;      // bring-up override
+    if (k <= 5 && slots == 3) {
+        rc = (pair == 2) ? launch_tc<5, 2, 3>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream)
+                         : launch_tc<5, 1, 3>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream);
+    } else if (k <= 5) {
+        rc = (pair == 2) ? launch_tc<5, 2, 2>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream)
+                         : launch_tc<5, 1, 2>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream);
     } else {
-        rc = (pair == 2) ? launch_tc<10, 2>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream)
-                         : launch_tc<10, 1>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream);
+        rc = (pair == 2) ? launch_tc<10, 2, 2>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream)
+                         : launch_tc<10, 1, 2>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream);
     }
     if (prof) cudaEventRecord(stop_ev, stream);
     return rc;
 }
 
 }  // namespace lys
+
+// bring-up hook (not part of the documented ABI): cycles per phase accumulated by kernels launched
+// with LYS_TC_TIMING set; reading resets the counters
+extern "C" __attribute__((visibility("default"))) int lys_debug_tc_timing(unsigned long long* out16)
+{
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out16, lys::g_tc_timing, sizeof(unsigned long long) * 16) != cudaSuccess) return -2;
+    unsigned long long zero[16] = {0};
+    if (cudaMemcpyToSymbol(lys::g_tc_timing, zero, sizeof(zero)) != cudaSuccess) return -2;
+    return 0;
+}
