@@ -48,6 +48,9 @@
 namespace lys {
 
 bool profile_begin(cudaStream_t st, const char* name, cudaEvent_t* stop_out);
+int bomp_encode_tc3(const float* X, int64_t xfs, int64_t xss, const float* D, int64_t ldd, const float* G,
+                    int n, int K, int64_t N, int k, int32_t* idx, float* val, int32_t* nsel,
+                    float* Z, int64_t zss, void* planes_ws, float* Dt, float* scratch, cudaStream_t stream);
 
 namespace {
 
@@ -261,6 +264,8 @@ __device__ __forceinline__ void update_step(SigState<KNZ>& st, int pick, bool la
 // registers per signal thread; NS = 2 leaves 232 (used for k > 5, whose Cholesky state is larger).
 // bring-up instrumentation (LYS_TC_TIMING=1): cycles per role/phase, summed over warps (lane 0)
 __device__ unsigned long long g_tc_timing[16];
+__device__ unsigned long long g_tc_trace[8192];      // CTA 0: (clock << 8 | warp << 4 | phase) of every lap
+__device__ unsigned int g_tc_trace_n;
 template <bool ON> struct PhaseTimer {
     long long t;
     __device__ __forceinline__ void start() { if (ON) t = clock64(); }
@@ -268,7 +273,13 @@ template <bool ON> struct PhaseTimer {
     {
         if (ON) {
             const long long now = clock64();
-            if (lane == 0) atomicAdd(&g_tc_timing[phase], (unsigned long long)(now - t));
+            if (lane == 0) {
+                atomicAdd(&g_tc_timing[phase], (unsigned long long)(now - t));
+                if (blockIdx.x == 0 && ((threadIdx.x >> 5) & 3) == 0) {
+                    const unsigned int i = atomicAdd(&g_tc_trace_n, 1u);
+                    if (i < 8192) g_tc_trace[i] = ((unsigned long long)now << 8) | ((threadIdx.x >> 5) << 4) | (unsigned)phase;
+                }
+            }
             t = now;
         }
     }
@@ -661,6 +672,9 @@ int bomp_encode_fused(const float* X, int64_t xfs, int64_t xss, const float* D, 
     unsigned char* planes = reinterpret_cast<unsigned char*>(workspace);
     float* Dt = reinterpret_cast<float*>(planes + align_up(planes_bytes(K), 256));
     float* scratch = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Dt) + align_up(dt_bytes(K), 256));
+    static const int ver = getenv("LYS_TC_VER") ? atoi(getenv("LYS_TC_VER")) : 1;           // bring-up override
+    if (ver == 3 && (K % 128) == 0)
+        return bomp_encode_tc3(X, xfs, xss, D, ldd, G, n, K, N, k, idx, val, nsel, Z, zss, planes, Dt, scratch, stream);
     const int pair = (K > 2 * CH) ? 2 : 1;
     const int nch = K / CH;
     const int items = K * (NF / 8);
@@ -695,5 +709,15 @@ extern "C" __attribute__((visibility("default"))) int lys_debug_tc_timing(unsign
     if (cudaMemcpyFromSymbol(out16, lys::g_tc_timing, sizeof(unsigned long long) * 16) != cudaSuccess) return -2;
     unsigned long long zero[16] = {0};
     if (cudaMemcpyToSymbol(lys::g_tc_timing, zero, sizeof(zero)) != cudaSuccess) return -2;
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int lys_debug_tc_trace(unsigned long long* out8192, unsigned int* n)
+{
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out8192, lys::g_tc_trace, sizeof(unsigned long long) * 8192) != cudaSuccess) return -2;
+    if (cudaMemcpyFromSymbol(n, lys::g_tc_trace_n, sizeof(unsigned int)) != cudaSuccess) return -2;
+    unsigned int z = 0;
+    if (cudaMemcpyToSymbol(lys::g_tc_trace_n, &z, sizeof(z)) != cudaSuccess) return -2;
     return 0;
 }

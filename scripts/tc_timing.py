@@ -21,11 +21,16 @@ def enc(dense=True):
                                       idx.data_ptr(), val.data_ptr(), nsel.data_ptr(), Zt.data_ptr() if dense else None, 1, K, ws.data_ptr(), wsb, st))
 out = (ctypes.c_ulonglong * 16)()
 dbg = lib.lys_debug_tc_timing
+trace = (ctypes.c_ulonglong * 8192)(); ntr = ctypes.c_uint()
 for dense in (True, False):
     enc(dense); torch.cuda.synchronize(); dbg(out)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); enc(dense); e1.record(); torch.cuda.synchronize()
     dbg(out)
+    lib.lys_debug_tc_trace(trace, ctypes.byref(ntr))
+    with open(os.path.join(ROOT, "gpurun_out", "tc_trace_%s_%s.txt" % (os.environ.get("LYS_TC_SLOTS", "2"), "dense" if dense else "sparse")), "w") as fh:
+        for i in range(min(int(ntr.value), 8192)):
+            e = int(trace[i]); fh.write("%d %d %d\n" % (e >> 8, (e >> 4) & 15, e & 15))
     v = [int(x) for x in out]
     names = ["tile start", "zero fill", "wait acc_full", "scan", "finish+update", "outputs", "", "", "mma: wait a_ready", "mma: wait acc_empty", "mma: issue"]
     print("slots=%s K=%d k=%d dense=%s: %.3f ms" % (os.environ.get("LYS_TC_SLOTS", "3"), K, k, dense, e0.elapsed_time(e1)))
