@@ -57,11 +57,18 @@ namespace {
 using namespace tc;
 
 constexpr int TM = 128;                  // signals per tile
-constexpr int CH = 256;                  // atoms per MMA chunk / TMEM stage
+// atoms per MMA / accumulator stage and number of stages in tensor memory (CH * NSTG = 512 columns).
+// Measured at cfg2: 2 x 256 beats 4 x 128 (1.43 vs 1.69 ms sparse): per-unit hand-shakes cost more than
+// the deeper pipeline hides.
+#ifndef LYS_CH
+#define LYS_CH 256
+#endif
+constexpr int CH = LYS_CH;
+constexpr int NSTG = 512 / CH;
 constexpr int NF = 64;                   // feature extent of the MMA (n <= 64, zero padded)
 constexpr int A_PLANE = TM * NF * 2;     // 16 KB: one fp16 plane of a residual tile
 constexpr int A_SLOT = 2 * A_PLANE;      // hi + lo
-constexpr int SMEM_BAR = 256;
+constexpr int SMEM_BAR = 384;
 constexpr int MAX_SLOTS = 3;
 constexpr float kDictScale = 32.f;       // atoms (unit norm) are stored as 32*d: fp16 lo plane stays normal
 
@@ -69,7 +76,6 @@ template <int PAIR> struct Geo {
     static constexpr int ROWS_B = CH / PAIR;            // atoms of one chunk held by one CTA
     static constexpr int B_PLANE = ROWS_B * NF * 2;     // bytes of one fp16 plane of one chunk in one CTA
     static constexpr int B_CHUNK = 2 * B_PLANE;
-    static constexpr int MAX_NCH = 2 * PAIR;            // 128 KB of planes per CTA
 };
 
 // kind::f16 instruction descriptor: D = F32, A = B = F16, both K-major
@@ -114,38 +120,50 @@ template <> struct Tree3<1> {
     static __device__ __forceinline__ float vmin(const float (&a)[1]) { return a[0]; }
 };
 
-template <int PIECE> struct ArgmaxState {
+__device__ __forceinline__ float piece_absmax(const uint32_t (&r)[32])
+{
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fabsf(__uint_as_float(r[i]));
+    return Tree3<32>::vmax(v);
+}
+
+// first-maximum argmax state of one signal: the winning 32-column piece is kept in registers as 2*v
+// (exact; a multiply runs on the full-rate FMA pipe, a MOV would queue behind the max tree on the
+// half-rate ALU pipe: FMNMX3 2.0, FMUL 0.5-1.0 cycles per warp instruction, scripts/ubench/pipes.cu)
+struct ArgmaxStateR {
     float run_max;
     int run_piece;
-    uint32_t kept[PIECE];
+    uint32_t kept[32];
 };
-
-template <int PIECE>
-__device__ __forceinline__ void scan_piece(const uint32_t (&r)[PIECE], int piece, ArgmaxState<PIECE>& am)
+__device__ __forceinline__ void scan_piece_r(const uint32_t (&r)[32], int piece, ArgmaxStateR& am)
 {
-    float v[PIECE];
-#pragma unroll
-    for (int i = 0; i < PIECE; ++i) v[i] = fabsf(__uint_as_float(r[i]));
-    const float m = Tree3<PIECE>::vmax(v);
+    const float m = piece_absmax(r);
     if (m > am.run_max) {
         am.run_max = m;
         am.run_piece = piece;
-        // keep 2*v (exact): a multiply runs on the full-rate FMA pipe, a MOV would queue behind the
-        // max tree on the half-rate ALU pipe (measured: FMNMX3 2.0, FMUL 0.5-1.0 cycles per warp instruction)
 #pragma unroll
-        for (int i = 0; i < PIECE; ++i) am.kept[i] = __float_as_uint(2.0f * __uint_as_float(r[i]));
+        for (int i = 0; i < 32; ++i) am.kept[i] = __float_as_uint(2.0f * __uint_as_float(r[i]));
     }
 }
-
-template <int PIECE>
-__device__ __forceinline__ int argmax_finish(const ArgmaxState<PIECE>& am)
+__device__ __forceinline__ int argmax_finish_r(const ArgmaxStateR& am)
 {
-    float key[PIECE];
+    float key[32];
     const float m2 = 2.0f * am.run_max;
 #pragma unroll
-    for (int i = 0; i < PIECE; ++i) key[i] = fmaf(fabsf(__uint_as_float(am.kept[i])) - m2, -1.0e30f, (float)i);
-    return am.run_piece * PIECE + (int)Tree3<PIECE>::vmin(key);
+    for (int i = 0; i < 32; ++i) key[i] = fmaf(fabsf(__uint_as_float(am.kept[i])) - m2, -1.0e30f, (float)i);
+    return am.run_piece * 32 + (int)Tree3<32>::vmin(key);
 }
+
+#ifndef LYS_ZGROUPS
+#define LYS_ZGROUPS 1
+#endif
+#ifndef LYS_ZSLEEP
+#define LYS_ZSLEEP 2000
+#endif
+#ifndef LYS_ZHINT
+#define LYS_ZHINT 1
+#endif
 
 // scale r by a power of two so that max|r| lands in [16,32), split into fp16 hi/lo planes and
 // store row `row` of the slot's A operand (canonical K-major no-swizzle layout: 16-byte chunk
@@ -259,9 +277,6 @@ __device__ __forceinline__ void update_step(SigState<KNZ>& st, int pick, bool la
     store_planes(slotA, row, st.r);
 }
 
-// NS = tiles ("slots") interleaved per CTA: NS signal warpgroups + one warpgroup holding the MMA warp.
-// NS = 3 needs 96 KB of residual planes next to the 128 KB of dictionary planes and leaves 160
-// registers per signal thread; NS = 2 leaves 232 (used for k > 5, whose Cholesky state is larger).
 // bring-up instrumentation (LYS_TC_TIMING=1): cycles per role/phase, summed over warps (lane 0)
 __device__ unsigned long long g_tc_timing[16];
 __device__ unsigned long long g_tc_trace[8192];      // CTA 0: (clock << 8 | warp << 4 | phase) of every lap
@@ -285,8 +300,12 @@ template <bool ON> struct PhaseTimer {
     }
 };
 
-template <int KNZ, int PAIR, int NS, bool TIMING>
-__global__ void __launch_bounds__((NS + 1) * 128, 1)
+constexpr int NS = 2;                    // tiles ("slots") interleaved per CTA
+constexpr int THREADS = (NS + 1) * 128;
+constexpr int ZB = 16384;                // block of zeros, source of the bulk stores that zero-fill dense rows
+
+template <int KNZ, int PAIR, bool TIMING>
+__global__ void __launch_bounds__(THREADS, 1)
 bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                const uint4* __restrict__ planes, const float* __restrict__ Dt, const float* __restrict__ G,
                int K, int nch, int64_t N, int k, int n_units /* clusters */, int rounds,
@@ -294,17 +313,14 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                float* __restrict__ Z, int64_t zss, float* __restrict__ scratch)
 {
     using GE = Geo<PAIR>;
-    constexpr int THREADS = (NS + 1) * 128;
-    constexpr int PIECE = (NS == 3) ? 16 : 32;       // TMEM columns per tcgen05.ld
-    constexpr int NP = CH / PIECE;
+    constexpr int NP = CH / 32;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sB = smem;
     unsigned char* sA = smem + (size_t)nch * GE::B_CHUNK;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sA + NS * A_SLOT);
-    // bars[slot] a_ready, [4 + 4 slot + chunk] acc_full, [16 + 4 slot + chunk] acc_empty; then the TMEM base
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
-    // block of zeros, source of the bulk (TMA) stores that zero-fill the dense code rows
-    constexpr int ZB = (NS == 3) ? 2048 : 16384;
+    // bars[slot] a_ready, [2 + slot] tile_begin, [4 + slot] zf_done, [8 + 8 slot + chunk] acc_full,
+    // [24 + 8 slot + chunk] acc_empty; then the TMEM base
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
     unsigned char* zbuf = reinterpret_cast<unsigned char*>(bars) + SMEM_BAR;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -313,8 +329,12 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
     const int64_t n_tiles = (N + TM - 1) / TM;
 
     if (tid == 0) {
-        for (int b = 0; b < NS; ++b) mbar_init(smem_u32(&bars[b]), 4 * PAIR);
-        for (int b = 0; b < 4 * NS; ++b) { mbar_init(smem_u32(&bars[4 + b]), 1); mbar_init(smem_u32(&bars[16 + b]), 4 * PAIR); }
+        for (int b = 0; b < NS; ++b) {
+            mbar_init(smem_u32(&bars[b]), 4 * PAIR);
+            mbar_init(smem_u32(&bars[2 + b]), 4);
+            mbar_init(smem_u32(&bars[4 + b]), 1);
+        }
+        for (int b = 0; b < 8 * NS; ++b) { mbar_init(smem_u32(&bars[8 + b]), 1); mbar_init(smem_u32(&bars[24 + b]), 4 * PAIR); }
         mbar_init_fence();
     }
     if (warp == 4 * NS) tmem_alloc<PAIR>(smem_u32(tmem_slot), 512);
@@ -334,63 +354,120 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
     // barrier addresses: waits are local, arrivals of a_ready / acc_empty go to the leader CTA
     const uint32_t bar_local = smem_u32(&bars[0]);
     const uint32_t bar_lead = mapa(bar_local, 0);
+    const uint32_t bar_self = mapa(bar_local, rank);
 
     if (warp >= 4 * NS) {
-        // ------------------------------------------------------------------- MMA issuer
-        // (the other three warps of this warpgroup only exist so that it can hand its registers over)
-        if constexpr (NS == 3) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
-        else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (warp == 4 * NS && rank == 0 && lane == 0) {
-            const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-            constexpr uint32_t LBO_A = TM * 16, LBO_B = GE::ROWS_B * 16, SBO = 128;
-            constexpr uint32_t kIdesc = make_idesc<PAIR>();
-            uint32_t u = 0;
-            uint32_t prev_bar0 = 0u, prev_bar1 = 0u, prev_par0 = 0u, prev_par1 = 0u;   // who used each TMEM stage last
-            PhaseTimer<TIMING> pt;
-            pt.start();
-            for (int r = 0; r < rounds; ++r) {
-                for (int j = 0; j < k; ++j) {
-                    const uint32_t q = (uint32_t)(r * k + j);
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == 4 * NS) {
+            // ------------------------------------------------------------------- MMA issuer
+            if (rank == 0 && lane == 0) {
+                const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+                constexpr uint32_t LBO_A = TM * 16, LBO_B = GE::ROWS_B * 16, SBO = 128;
+                constexpr uint32_t kIdesc = make_idesc<PAIR>();
+                uint32_t u = 0;
+                uint32_t pb0 = 0u, pb1 = 0u, pb2 = 0u, pb3 = 0u, pp0 = 0u, pp1 = 0u, pp2 = 0u, pp3 = 0u;   // who used each TMEM stage last
+                PhaseTimer<TIMING> pt;
+                pt.start();
+                for (int r = 0; r < rounds; ++r) {
+                    for (int j = 0; j < k; ++j) {
+                        const uint32_t q = (uint32_t)(r * k + j);
 #pragma unroll 1
-                    for (int s = 0; s < NS; ++s) {
-                        mbar_wait(bar_local + 8 * s, q & 1);                         // planes of r_j landed (both CTAs)
-                        fence_after();
-                        pt.lap(8, 0);
+                        for (int s = 0; s < NS; ++s) {
+                            mbar_wait(bar_local + 8 * s, q & 1);                  // planes of r_j landed (both CTAs)
+                            fence_after();
+                            pt.lap(8, 0);
 #pragma unroll 1
-                        for (int c = 0; c < nch; ++c, ++u) {
-                            const uint32_t stg = u & 1;
-                            if (u >= 2) {                                              // stage drained (both CTAs)
-                                mbar_wait(stg ? prev_bar1 : prev_bar0, stg ? prev_par1 : prev_par0);
-                                fence_after();
+                            for (int c = 0; c < nch; ++c, ++u) {
+                                const uint32_t stg = u & (NSTG - 1);
+                                if (u >= NSTG) {                                       // stage drained (both CTAs)
+                                    mbar_wait(stg == 0 ? pb0 : stg == 1 ? pb1 : stg == 2 ? pb2 : pb3,
+                                              stg == 0 ? pp0 : stg == 1 ? pp1 : stg == 2 ? pp2 : pp3);
+                                    fence_after();
+                                }
+                                pt.lap(9, 0);
+                                const uint32_t eb = bar_local + 8 * (24 + 8 * s + c);
+                                if (stg == 0) { pb0 = eb; pp0 = q & 1; } else if (stg == 1) { pb1 = eb; pp1 = q & 1; }
+                                else if (stg == 2) { pb2 = eb; pp2 = q & 1; } else { pb3 = eb; pp3 = q & 1; }
+                                const uint32_t d_tmem = tmem_base + stg * CH;
+                                const uint32_t a_hi = a_base + s * A_SLOT, a_lo = a_hi + A_PLANE;
+                                const uint32_t b_hi = b_base + (c * 2) * GE::B_PLANE, b_lo = b_hi + GE::B_PLANE;
+                                // small products first: (lo,hi) (hi,lo) (hi,hi)
+#pragma unroll
+                                for (int ks = 0; ks < NF / 16; ++ks)
+                                    mma_f16<PAIR>(d_tmem, make_desc(a_lo + ks * 2 * LBO_A, LBO_A, SBO), make_desc(b_hi + ks * 2 * LBO_B, LBO_B, SBO), kIdesc, ks > 0);
+#pragma unroll
+                                for (int ks = 0; ks < NF / 16; ++ks)
+                                    mma_f16<PAIR>(d_tmem, make_desc(a_hi + ks * 2 * LBO_A, LBO_A, SBO), make_desc(b_lo + ks * 2 * LBO_B, LBO_B, SBO), kIdesc, 1);
+#pragma unroll
+                                for (int ks = 0; ks < NF / 16; ++ks)
+                                    mma_f16<PAIR>(d_tmem, make_desc(a_hi + ks * 2 * LBO_A, LBO_A, SBO), make_desc(b_hi + ks * 2 * LBO_B, LBO_B, SBO), kIdesc, 1);
+                                commit<PAIR>(bar_local + 8 * (8 + 8 * s + c));        // accumulator ready
+                                pt.lap(10, 0);
                             }
-                            pt.lap(9, 0);
-                            const uint32_t eb = bar_local + 8 * (16 + 4 * s + c);
-                            if (stg) { prev_bar1 = eb; prev_par1 = q & 1; } else { prev_bar0 = eb; prev_par0 = q & 1; }
-                            const uint32_t d_tmem = tmem_base + stg * CH;
-                            const uint32_t a_hi = a_base + s * A_SLOT, a_lo = a_hi + A_PLANE;
-                            const uint32_t b_hi = b_base + (c * 2) * GE::B_PLANE, b_lo = b_hi + GE::B_PLANE;
-                            // small products first: (lo,hi) (hi,lo) (hi,hi)
-#pragma unroll
-                            for (int ks = 0; ks < NF / 16; ++ks)
-                                mma_f16<PAIR>(d_tmem, make_desc(a_lo + ks * 2 * LBO_A, LBO_A, SBO), make_desc(b_hi + ks * 2 * LBO_B, LBO_B, SBO), kIdesc, ks > 0);
-#pragma unroll
-                            for (int ks = 0; ks < NF / 16; ++ks)
-                                mma_f16<PAIR>(d_tmem, make_desc(a_hi + ks * 2 * LBO_A, LBO_A, SBO), make_desc(b_lo + ks * 2 * LBO_B, LBO_B, SBO), kIdesc, 1);
-#pragma unroll
-                            for (int ks = 0; ks < NF / 16; ++ks)
-                                mma_f16<PAIR>(d_tmem, make_desc(a_hi + ks * 2 * LBO_A, LBO_A, SBO), make_desc(b_hi + ks * 2 * LBO_B, LBO_B, SBO), kIdesc, 1);
-                            commit<PAIR>(bar_local + 8 * (4 + 4 * s + c));            // accumulator ready
-                            pt.lap(10, 0);
                         }
                     }
                 }
             }
+            __syncwarp();
+        } else if (Z && warp <= 4 * NS + NS) {
+            // ------------------------------------------------------- zero fill of the dense rows (:308)
+            // one otherwise idle warp per slot: bulk (TMA) stores from the block of zeros while the signal
+            // warps of the slot work through the tile's greedy steps.  The 512 KB of a tile go out in
+            // ZGROUPS paced groups (a burst of all of it saturates the HBM write path and stalls every
+            // gather of the SM's other warps) with an L2 evict-first policy (4 GB of zeros per million
+            // signals stream through L2 next to a 30 MB hot set: Gram rows, atoms, direction scratch).
+            const int zs = warp - 4 * NS - 1;
+            const uint32_t zsrc = smem_u32(zbuf);
+            uint64_t pol;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+            for (int r = 0; r < rounds; ++r) {
+                mbar_wait(bar_local + 8 * (2 + zs), (uint32_t)r & 1);             // the slot has started this tile
+                const int64_t tile = (((int64_t)r * n_units + unit) * PAIR + rank) * NS + zs;
+                const int64_t sig0 = tile * TM;
+                if (tile < n_tiles) {
+                    const int64_t rows = (N - sig0 < TM) ? (N - sig0) : TM;
+                    const int row_bytes = K * 4;
+                    const bool contiguous = (zss == K);
+                    // op i covers bytes [i*ZB, (i+1)*ZB) of the tile (contiguous) or of a row (strided rows)
+                    const int per_row = (row_bytes + ZB - 1) / ZB;
+                    const int64_t n_ops = contiguous ? (rows * row_bytes + ZB - 1) / ZB : rows * per_row;
+                    const int64_t per_group = ((n_ops + LYS_ZGROUPS - 1) / LYS_ZGROUPS + 31) / 32 * 32;
+                    for (int64_t g0 = 0; g0 < n_ops; g0 += per_group) {
+                        const int64_t g1 = (g0 + per_group < n_ops) ? g0 + per_group : n_ops;
+                        for (int64_t op = g0 + lane; op < g1; op += 32) {
+                            char* gp; int64_t bytes;
+                            if (contiguous) {
+                                const int64_t off = op * ZB, total = rows * row_bytes;
+                                gp = reinterpret_cast<char*>(Z + sig0 * zss) + off;
+                                bytes = (total - off < ZB) ? (total - off) : ZB;
+                            } else {
+                                const int64_t rr = op / per_row; const int off = (int)(op % per_row) * ZB;
+                                gp = reinterpret_cast<char*>(Z + (sig0 + rr) * zss) + off;
+                                bytes = (row_bytes - off < ZB) ? (row_bytes - off) : ZB;
+                            }
+#if LYS_ZHINT
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                                         ::"l"(gp), "r"(zsrc), "r"((uint32_t)bytes), "l"(pol) : "memory");
+#else
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                         ::"l"(gp), "r"(zsrc), "r"((uint32_t)bytes) : "memory");
+#endif
+                        }
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#if LYS_ZGROUPS > 1
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        __nanosleep(LYS_ZSLEEP);
+#endif
+                    }
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(bar_self + 8 * (4 + zs));
+            }
         }
-        __syncwarp();
     } else {
         // ------------------------------------------------------------- one thread = one signal
-        if constexpr (NS == 3) asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
-        else asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
         const int s = warp >> 2;                      // slot
         const int quad = warp & 3;                    // TMEM lane quadrant of this warp
         const int row = quad * 32 + lane;             // row of the tile
@@ -425,91 +502,49 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
             store_planes(slotA, row, st.r);
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * s);
+            if (lane == 0) {
+                mbar_arrive_cluster(bar_lead + 8 * s);
+                if (Z) mbar_arrive_cluster(bar_self + 8 * (2 + s));
+            }
             st.cnt = 0;
             st.done = !live;
             pt.lap(0, lane);
-            const int64_t sig0 = tile * TM + quad * 32;          // first of this warp's 32 signals
             for (int j = 0; j < k; ++j) {
-                // ---- dense rows (:308): zero fill of this warp's 32 rows by bulk (TMA) stores from the block
-                // of zeros in shared memory, a k-th per step: no LSU traffic, no warp stalls.  The
-                // coefficients are scattered after the last step, once the bulk stores have completed.
-                if (Z && tile < n_tiles && lane == 0 && sig0 < N) {
-                    const int64_t rows = (N - sig0 < 32) ? (N - sig0) : 32;
-                    const bool contiguous = (zss == K);
-                    const int64_t total = rows * K * 4;
-                    const int nseg = contiguous ? (int)((total + ZB - 1) / ZB) : (int)rows * ((K * 4 + ZB - 1) / ZB);
-                    const int per_row = (K * 4 + ZB - 1) / ZB;
-                    const int s1 = (int)(((int64_t)nseg * (j + 1)) / k);
-                    for (int sg = (int)(((int64_t)nseg * j) / k); sg < s1; ++sg) {
-                        char* gp; int64_t bytes;
-                        if (contiguous) {
-                            gp = reinterpret_cast<char*>(Z + sig0 * zss) + (int64_t)sg * ZB;
-                            bytes = (total - (int64_t)sg * ZB < ZB) ? total - (int64_t)sg * ZB : ZB;
-                        } else {
-                            const int rr = sg / per_row, part = sg % per_row;
-                            gp = reinterpret_cast<char*>(Z + (sig0 + rr) * zss) + (int64_t)part * ZB;
-                            bytes = ((int64_t)K * 4 - (int64_t)part * ZB < ZB) ? (int64_t)K * 4 - (int64_t)part * ZB : ZB;
-                        }
-                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                     ::"l"(gp), "r"(smem_u32(zbuf)), "r"((uint32_t)bytes) : "memory");
-                    }
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-                pt.lap(1, lane);
                 // ---- :322 argmax |alpha_j| over all atoms, first maximum
-                ArgmaxState<PIECE> am;
+                ArgmaxStateR am;
                 am.run_max = -1.f;
                 am.run_piece = 0;
 #pragma unroll
-                for (int i = 0; i < PIECE; ++i) am.kept[i] = 0u;
-                const uint32_t u0 = (uint32_t)(((r * k + j) * NS + s) * nch);
+                for (int i = 0; i < 32; ++i) am.kept[i] = 0u;
+                const uint32_t qq = (uint32_t)(r * k + j);
+                const uint32_t u0 = (qq * NS + s) * (uint32_t)nch;
 #pragma unroll 1
                 for (int c = 0; c < nch; ++c) {
-                    const uint32_t stg = (u0 + c) & 1;
-                    mbar_wait(bar_local + 8 * (4 + 4 * s + c), (uint32_t)(r * k + j) & 1);
+                    const uint32_t stg = (u0 + c) & (NSTG - 1);
+                    mbar_wait(bar_local + 8 * (8 + 8 * s + c), qq & 1);
                     fence_after();
                     pt.lap(2, lane);
                     const uint32_t ta = tq + stg * CH;
-                    uint32_t b0[PIECE], b1[PIECE];
-                    if constexpr (PIECE == 32) {
-                        LYS_TMEM_LD_X32(ta, b0);
+                    uint32_t b0[32], b1[32];
+                    LYS_TMEM_LD_X32(ta, b0);
 #pragma unroll
-                        for (int sc = 0; sc < NP; sc += 2) {
-                            LYS_TMEM_WAIT_X32(b0);
-                            LYS_TMEM_LD_X32(ta + (sc + 1) * PIECE, b1);
-                            scan_piece<PIECE>(b0, c * NP + sc, am);
-                            LYS_TMEM_WAIT_X32(b1);
-                            if (sc + 2 < NP) LYS_TMEM_LD_X32(ta + (sc + 2) * PIECE, b0);
-                            else {
-                                // every tcgen05.ld of this stage has completed: hand it back to the MMA issuer
-                                fence_before();
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * (16 + 4 * s + c));
-                            }
-                            scan_piece<PIECE>(b1, c * NP + sc + 1, am);
+                    for (int sc = 0; sc < NP; sc += 2) {
+                        LYS_TMEM_WAIT_X32(b0);
+                        LYS_TMEM_LD_X32(ta + (sc + 1) * 32, b1);
+                        scan_piece_r(b0, c * NP + sc, am);
+                        LYS_TMEM_WAIT_X32(b1);
+                        if (sc + 2 < NP) LYS_TMEM_LD_X32(ta + (sc + 2) * 32, b0);
+                        else {
+                            fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * (24 + 8 * s + c));
                         }
-                    } else {
-                        LYS_TMEM_LD_X16(ta, b0);
-#pragma unroll
-                        for (int sc = 0; sc < NP; sc += 2) {
-                            LYS_TMEM_WAIT_X16(b0);
-                            LYS_TMEM_LD_X16(ta + (sc + 1) * PIECE, b1);
-                            scan_piece<PIECE>(b0, c * NP + sc, am);
-                            LYS_TMEM_WAIT_X16(b1);
-                            if (sc + 2 < NP) LYS_TMEM_LD_X16(ta + (sc + 2) * PIECE, b0);
-                            else {
-                                fence_before();
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * (16 + 4 * s + c));
-                            }
-                            scan_piece<PIECE>(b1, c * NP + sc + 1, am);
-                        }
+                        scan_piece_r(b1, c * NP + sc + 1, am);
                     }
                     pt.lap(3, lane);
                 }
                 const bool last = (j + 1 >= k);
-                const int run_idx = argmax_finish<PIECE>(am);
+                const int run_idx = argmax_finish_r(am);
                 if (!st.done) {
                     switch (j) {
 #define LYS_STEP(JJ) case JJ: if constexpr (JJ < KNZ) update_step<JJ, KNZ>(st, run_idx, last, k, Dt, G, K, U, slotA, row); break;
@@ -527,8 +562,7 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                 pt.lap(4, lane);
             }
             // ---- :354 z = L^-T y, outputs
-            if (Z && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-            __syncwarp();                   // this warp's zero fill is complete before any lane scatters
+            if (Z) mbar_wait(bar_local + 8 * (4 + s), (uint32_t)r & 1);          // dense rows of this tile are zeroed
             if (live) {
                 float z[KNZ];
 #pragma unroll
@@ -602,7 +636,7 @@ __global__ void prep_dict_kernel(const float* __restrict__ D, int64_t ldd, int n
 bool fused_shape_ok(int n, int K, int k)
 {
     if (const char* e = getenv("LYS_BOMP_PATH")) if (!strcmp(e, "legacy")) return false;
-    return n >= 1 && n <= NF && K >= CH && (K % CH) == 0 && K <= 4 * CH && k >= 1 && k <= 10;
+    return n >= 1 && n <= NF && K >= CH && (K % CH) == 0 && K <= 1024 && k >= 1 && k <= 10;
 }
 
 size_t planes_bytes(int K) { return (size_t)K * NF * 2 * 2; }      // hi + lo fp16 of every atom
@@ -610,17 +644,16 @@ size_t dt_bytes(int K) { return (size_t)K * NF * sizeof(float); }
 // orthonormalised directions u_0..u_{k-3} of every signal in flight: [CTA][slot][vector][feature][signal]
 size_t scratch_bytes(int k) { return (size_t)sm_count() * MAX_SLOTS * (k > 2 ? k - 2 : 0) * NF * TM * sizeof(float); }
 
-template <int KNZ, int PAIR, int NS>
+template <int KNZ, int PAIR>
 int launch_tc(const float* X, int64_t xfs, int64_t xss, int n, const void* planes, const float* Dt, const float* G,
               int K, int64_t N, int k, int32_t* idx, float* val, int32_t* nsel, float* Z, int64_t zss,
               float* scratch, cudaStream_t stream)
 {
     using GE = Geo<PAIR>;
     const int nch = K / CH;
-    constexpr int THREADS = (NS + 1) * 128;
-    const size_t smem = (size_t)nch * GE::B_CHUNK + (size_t)NS * A_SLOT + SMEM_BAR + (NS == 3 ? 2048 : 16384);
+    const size_t smem = (size_t)nch * GE::B_CHUNK + (size_t)NS * A_SLOT + SMEM_BAR + ZB;
     static const bool timing = getenv("LYS_TC_TIMING") != nullptr;
-    auto kern = timing ? bomp_tc_kernel<KNZ, PAIR, NS, true> : bomp_tc_kernel<KNZ, PAIR, NS, false>;
+    auto kern = timing ? bomp_tc_kernel<KNZ, PAIR, true> : bomp_tc_kernel<KNZ, PAIR, false>;
     LYS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n_tiles = (N + TM - 1) / TM;
     const int64_t tiles_per_unit = (int64_t)PAIR * NS;
@@ -675,7 +708,7 @@ int bomp_encode_fused(const float* X, int64_t xfs, int64_t xss, const float* D, 
     static const int ver = getenv("LYS_TC_VER") ? atoi(getenv("LYS_TC_VER")) : 1;           // bring-up override
     if (ver == 3 && (K % 128) == 0)
         return bomp_encode_tc3(X, xfs, xss, D, ldd, G, n, K, N, k, idx, val, nsel, Z, zss, planes, Dt, scratch, stream);
-    const int pair = (K > 2 * CH) ? 2 : 1;
+    const int pair = (K > 512) ? 2 : 1;
     const int nch = K / CH;
     const int items = K * (NF / 8);
     if (pair == 2) prep_dict_kernel<2><<<(items + 255) / 256, 256, 0, stream>>>(D, ldd, n, K, nch, planes, Dt);
@@ -684,16 +717,12 @@ int bomp_encode_fused(const float* X, int64_t xfs, int64_t xss, const float* D, 
     cudaEvent_t stop_ev;
     const bool prof = profile_begin(stream, "bomp_tc_kernel", &stop_ev);
     int rc;
-    static const int slots = getenv("LYS_TC_SLOTS") ? atoi(getenv("LYS_TC_SLOTS")) : 2;      // bring-up override
-    if (k <= 5 && slots == 3) {
-        rc = (pair == 2) ? launch_tc<5, 2, 3>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream)
-                         : launch_tc<5, 1, 3>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream);
-    } else if (k <= 5) {
-        rc = (pair == 2) ? launch_tc<5, 2, 2>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream)
-                         : launch_tc<5, 1, 2>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream);
+    if (k <= 5) {
+        rc = (pair == 2) ? launch_tc<5, 2>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream)
+                         : launch_tc<5, 1>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream);
     } else {
-        rc = (pair == 2) ? launch_tc<10, 2, 2>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream)
-                         : launch_tc<10, 1, 2>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream);
+        rc = (pair == 2) ? launch_tc<10, 2>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream)
+                         : launch_tc<10, 1>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream);
     }
     if (prof) cudaEventRecord(stop_ev, stream);
     return rc;
