@@ -310,7 +310,7 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                const uint4* __restrict__ planes, const float* __restrict__ Dt, const float* __restrict__ G,
                int K, int nch, int64_t N, int k, int n_units /* clusters */, int rounds,
                int32_t* __restrict__ idx, float* __restrict__ val, int32_t* __restrict__ nsel,
-               float* __restrict__ Z, int64_t zss, float* __restrict__ scratch)
+               float* __restrict__ Z, int64_t zss, float* __restrict__ scratch, int dbg)
 {
     using GE = Geo<PAIR>;
     constexpr int NP = CH / 32;
@@ -321,6 +321,7 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
     // bars[slot] a_ready, [2 + slot] tile_begin, [4 + slot] zf_done, [8 + 8 slot + chunk] acc_full,
     // [24 + 8 slot + chunk] acc_empty; then the TMEM base
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
+    uint32_t* tile_ready = tmem_slot + 2;              // [slot] signal warps that have published a tile's codes
     unsigned char* zbuf = reinterpret_cast<unsigned char*>(bars) + SMEM_BAR;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -329,6 +330,7 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
     const int64_t n_tiles = (N + TM - 1) / TM;
 
     if (tid == 0) {
+        tile_ready[0] = 0u; tile_ready[1] = 0u;
         for (int b = 0; b < NS; ++b) {
             mbar_init(smem_u32(&bars[b]), 4 * PAIR);
             mbar_init(smem_u32(&bars[2 + b]), 4);
@@ -344,7 +346,7 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
         uint4* dst = reinterpret_cast<uint4*>(sB);
         for (int it = tid; it < items; it += THREADS) dst[it] = __ldg(src + it);
     }
-    for (int it = tid; it < ZB / 16; it += THREADS) reinterpret_cast<uint4*>(zbuf)[it] = make_uint4(0u, 0u, 0u, 0u);
+    for (int it = tid; it < NS * ZB / 16; it += THREADS) reinterpret_cast<uint4*>(zbuf)[it] = make_uint4(0u, 0u, 0u, 0u);
     fence_async_smem();
     fence_before();
     __syncthreads();
@@ -354,8 +356,7 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
     // barrier addresses: waits are local, arrivals of a_ready / acc_empty go to the leader CTA
     const uint32_t bar_local = smem_u32(&bars[0]);
     const uint32_t bar_lead = mapa(bar_local, 0);
-    const uint32_t bar_self = mapa(bar_local, rank);
-
+    
     if (warp >= 4 * NS) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (warp == 4 * NS) {
@@ -410,60 +411,67 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
             }
             __syncwarp();
         } else if (Z && warp <= 4 * NS + NS) {
-            // ------------------------------------------------------- zero fill of the dense rows (:308)
-            // one otherwise idle warp per slot: bulk (TMA) stores from the block of zeros while the signal
-            // warps of the slot work through the tile's greedy steps.  The 512 KB of a tile go out in
-            // ZGROUPS paced groups (a burst of all of it saturates the HBM write path and stalls every
-            // gather of the SM's other warps) with an L2 evict-first policy (4 GB of zeros per million
-            // signals stream through L2 next to a 30 MB hot set: Gram rows, atoms, direction scratch).
+            // ------------------------------------------------------- dense code rows (:308, :365)
+            // One otherwise idle warp per slot writes the dense rows of a tile AFTER its signal warps have
+            // published the sparse codes: rows are composed in shared memory (a block of zeros + the k
+            // coefficients of each row) and leave with one bulk (TMA) store per ZROWS rows, so every
+            // byte of Z is written exactly once.  (Zero-filling first and scattering afterwards cost
+            // 0.5 ms per million signals: the 4-byte scatters hit lines that had already left L2.)
+            // The writer works one tile behind the signal warps; a counter in shared memory, not an
+            // mbarrier, tracks how many tiles are ready, so it may lag by any number of tiles.
             const int zs = warp - 4 * NS - 1;
-            const uint32_t zsrc = smem_u32(zbuf);
+            float* zf = reinterpret_cast<float*>(zbuf + zs * ZB);                  // this slot's row block
+            const uint32_t zsrc = smem_u32(zf);
+            volatile uint32_t* ready = tile_ready + zs;
             uint64_t pol;
             asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+            const int zrows = (zss == K) ? min(ZB / (K * 4), 64 / k) : 1;        // rows per bulk store (<= 64 codes)
             for (int r = 0; r < rounds; ++r) {
-                mbar_wait(bar_local + 8 * (2 + zs), (uint32_t)r & 1);             // the slot has started this tile
                 const int64_t tile = (((int64_t)r * n_units + unit) * PAIR + rank) * NS + zs;
                 const int64_t sig0 = tile * TM;
-                if (tile < n_tiles) {
-                    const int64_t rows = (N - sig0 < TM) ? (N - sig0) : TM;
-                    const int row_bytes = K * 4;
-                    const bool contiguous = (zss == K);
-                    // op i covers bytes [i*ZB, (i+1)*ZB) of the tile (contiguous) or of a row (strided rows)
-                    const int per_row = (row_bytes + ZB - 1) / ZB;
-                    const int64_t n_ops = contiguous ? (rows * row_bytes + ZB - 1) / ZB : rows * per_row;
-                    const int64_t per_group = ((n_ops + LYS_ZGROUPS - 1) / LYS_ZGROUPS + 31) / 32 * 32;
-                    for (int64_t g0 = 0; g0 < n_ops; g0 += per_group) {
-                        const int64_t g1 = (g0 + per_group < n_ops) ? g0 + per_group : n_ops;
-                        for (int64_t op = g0 + lane; op < g1; op += 32) {
-                            char* gp; int64_t bytes;
-                            if (contiguous) {
-                                const int64_t off = op * ZB, total = rows * row_bytes;
-                                gp = reinterpret_cast<char*>(Z + sig0 * zss) + off;
-                                bytes = (total - off < ZB) ? (total - off) : ZB;
-                            } else {
-                                const int64_t rr = op / per_row; const int off = (int)(op % per_row) * ZB;
-                                gp = reinterpret_cast<char*>(Z + (sig0 + rr) * zss) + off;
-                                bytes = (row_bytes - off < ZB) ? (row_bytes - off) : ZB;
-                            }
-#if LYS_ZHINT
-                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-                                         ::"l"(gp), "r"(zsrc), "r"((uint32_t)bytes), "l"(pol) : "memory");
-#else
-                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                         ::"l"(gp), "r"(zsrc), "r"((uint32_t)bytes) : "memory");
-#endif
-                        }
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-#if LYS_ZGROUPS > 1
-                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        __nanosleep(LYS_ZSLEEP);
-#endif
+                if (tile >= n_tiles) break;
+                while (*ready < 4u * (uint32_t)(r + 1)) __nanosleep(200);        // 4 signal warps per tile
+                __threadfence();
+                const int64_t rows = (N - sig0 < TM) ? (N - sig0) : TM;
+                // lane c (and c + 32) handles code c of a group: row c / k, selection slot c % k (zrows * k <= 64)
+                int a0 = -1, a1 = -1, o0 = 0, o1 = 0;
+                float v0 = 0.f, v1 = 0.f;
+                auto fetch = [&](int64_t g, int& fa0, float& fv0, int& fo0, int& fa1, float& fv1, int& fo1) {
+                    const int nr = (int)((rows - g < zrows) ? (rows - g) : zrows);
+                    fa0 = -1; fa1 = -1;
+                    if (g < rows && lane < nr * k) {
+                        const int64_t e = (sig0 + g) * k + lane;
+                        fa0 = __ldcg(idx + e); fv0 = __ldcg(val + e); fo0 = (lane / k) * K;
                     }
-                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                    if (g < rows && lane + 32 < nr * k) {
+                        const int64_t e = (sig0 + g) * k + lane + 32;
+                        fa1 = __ldcg(idx + e); fv1 = __ldcg(val + e); fo1 = ((lane + 32) / k) * K;
+                    }
+                };
+                fetch(0, a0, v0, o0, a1, v1, o1);
+                for (int64_t g = 0; g < rows; g += zrows) {
+                    const int nr = (int)((rows - g < zrows) ? (rows - g) : zrows);
+                    if (a0 >= 0) zf[o0 + a0] = v0;
+                    if (a1 >= 0) zf[o1 + a1] = v1;
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                                     ::"l"(Z + (sig0 + g) * zss), "r"(zsrc), "r"((uint32_t)(nr * K * 4)), "l"(pol) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    int na0, na1, no0 = 0, no1 = 0;
+                    float nv0 = 0.f, nv1 = 0.f;
+                    fetch(g + zrows, na0, nv0, no0, na1, nv1, no1);              // next group's codes while the TMA reads
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the block may be reused
+                    __syncwarp();
+                    if (a0 >= 0) zf[o0 + a0] = 0.f;
+                    if (a1 >= 0) zf[o1 + a1] = 0.f;
+                    __syncwarp();
+                    a0 = na0; v0 = nv0; o0 = no0; a1 = na1; v1 = nv1; o1 = no1;
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(bar_self + 8 * (4 + zs));
             }
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
     } else {
         // ------------------------------------------------------------- one thread = one signal
@@ -502,10 +510,7 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
             store_planes(slotA, row, st.r);
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive_cluster(bar_lead + 8 * s);
-                if (Z) mbar_arrive_cluster(bar_self + 8 * (2 + s));
-            }
+            if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * s);
             st.cnt = 0;
             st.done = !live;
             pt.lap(0, lane);
@@ -531,7 +536,7 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                     for (int sc = 0; sc < NP; sc += 2) {
                         LYS_TMEM_WAIT_X32(b0);
                         LYS_TMEM_LD_X32(ta + (sc + 1) * 32, b1);
-                        scan_piece_r(b0, c * NP + sc, am);
+                        if (!(dbg & 4)) scan_piece_r(b0, c * NP + sc, am);
                         LYS_TMEM_WAIT_X32(b1);
                         if (sc + 2 < NP) LYS_TMEM_LD_X32(ta + (sc + 2) * 32, b0);
                         else {
@@ -539,13 +544,13 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                             __syncwarp();
                             if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * (24 + 8 * s + c));
                         }
-                        scan_piece_r(b1, c * NP + sc + 1, am);
+                        if (!(dbg & 4)) scan_piece_r(b1, c * NP + sc + 1, am); else am.kept[sc] ^= b0[sc] ^ b1[sc + 1];
                     }
                     pt.lap(3, lane);
                 }
                 const bool last = (j + 1 >= k);
                 const int run_idx = argmax_finish_r(am);
-                if (!st.done) {
+                if (!st.done && !(dbg & 8)) {
                     switch (j) {
 #define LYS_STEP(JJ) case JJ: if constexpr (JJ < KNZ) update_step<JJ, KNZ>(st, run_idx, last, k, Dt, G, K, U, slotA, row); break;
                         LYS_STEP(0) LYS_STEP(1) LYS_STEP(2) LYS_STEP(3) LYS_STEP(4)
@@ -562,7 +567,6 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                 pt.lap(4, lane);
             }
             // ---- :354 z = L^-T y, outputs
-            if (Z) mbar_wait(bar_local + 8 * (4 + s), (uint32_t)r & 1);          // dense rows of this tile are zeroed
             if (live) {
                 float z[KNZ];
 #pragma unroll
@@ -582,10 +586,13 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                         const bool has = m < st.cnt;
                         idx[sig * k + m] = has ? st.sel[m] : -1;
                         val[sig * k + m] = has ? z[m] : 0.f;
-                        if (Z && has) Z[sig * zss + st.sel[m]] = z[m];
                     }
                 }
                 if (nsel) nsel[sig] = st.cnt;
+            }
+            if (Z && tile < n_tiles) {                 // hand the tile to the dense-row writer of this slot
+                __syncwarp();
+                if (lane == 0) { __threadfence(); atomicAdd(tile_ready + s, 1u); }
             }
             pt.lap(5, lane);
         }
@@ -651,7 +658,7 @@ int launch_tc(const float* X, int64_t xfs, int64_t xss, int n, const void* plane
 {
     using GE = Geo<PAIR>;
     const int nch = K / CH;
-    const size_t smem = (size_t)nch * GE::B_CHUNK + (size_t)NS * A_SLOT + SMEM_BAR + ZB;
+    const size_t smem = (size_t)nch * GE::B_CHUNK + (size_t)NS * A_SLOT + SMEM_BAR + NS * ZB;
     static const bool timing = getenv("LYS_TC_TIMING") != nullptr;
     auto kern = timing ? bomp_tc_kernel<KNZ, PAIR, true> : bomp_tc_kernel<KNZ, PAIR, false>;
     LYS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -678,7 +685,8 @@ int launch_tc(const float* X, int64_t xfs, int64_t xss, int n, const void* plane
     const int rounds = (int)((n_tiles + (int64_t)units * tiles_per_unit - 1) / ((int64_t)units * tiles_per_unit));
     cfg.gridDim = dim3((unsigned)(units * PAIR), 1, 1);
     LYS_CUDA(cudaLaunchKernelEx(&cfg, kern, X, xfs, xss, n, reinterpret_cast<const uint4*>(planes), Dt, G, K, nch, N, k,
-                                units, rounds, idx, val, nsel, Z, zss, scratch));
+                                units, rounds, idx, val, nsel, Z, zss, scratch,
+                                getenv("LYS_TC_DBG") ? atoi(getenv("LYS_TC_DBG")) : 0));
     LYS_LAUNCH_CHECK("bomp_tc_kernel");
     return LYS_OK;
 }
