@@ -201,3 +201,49 @@ def test_empty_and_errors():
         _enc(3).encode(torch.zeros((32, 5), device=DEV), D)              # feature mismatch
     with pytest.raises(_native.LyssaError):
         _enc(65).encode(torch.zeros((64, 5), device=DEV), D)             # k > K
+
+
+# ---- shapes served by the fused tcgen05 kernel (csrc/bomp_fused.cu): single-CTA (K <= 512) and CTA-pair
+# (K > 512) variants, zero-padded features (n < 64), ragged last tile, k = 1 .. 10
+@pytest.mark.parametrize("n,K,N,k", [(64, 512, 3001, 5), (64, 768, 2000, 3), (48, 512, 1000, 4), (64, 256, 130, 1),
+                                     (64, 1024, 257, 2), (64, 1024, 3000, 10), (20, 384, 500, 6)])
+def test_fused_kernel_shapes_vs_oracle(n, K, N, k):
+    X = lo.synthetic_patches(N, n, seed=300 + N % 89)
+    D = lo.synthetic_dictionary(K, n, seed=11 + K)
+    codes = _enc(k).encode_sparse(torch.from_numpy(np.ascontiguousarray(X)).to(DEV), torch.from_numpy(D).to(DEV))
+    idx_r, val_r, ok = _oracle_ok(X, D, k)
+    rep = parity.check_codes(codes.idx.cpu().numpy(), codes.val.cpu().numpy(), idx_r, val_r, ok,
+                             label="fused n%d K%d N%d k%d" % (n, K, N, k))
+    assert rep["excluded"] <= max(2, N // 100), rep
+
+
+def test_fused_kernel_dense_layouts():
+    """Dense Z from the fused kernel: contiguous rows, padded rows (z_sig_stride > K) and the sparse-only
+    call give the same codes; every element of Z is written exactly once (zeros included)."""
+    lib = _native.load()
+    n, K, N, k = 64, 1024, 1000, 5
+    Xh = lo.synthetic_patches(N, n, seed=5); Dh = lo.synthetic_dictionary(K, n, seed=6)
+    X = torch.from_numpy(np.ascontiguousarray(Xh.T)).to(DEV)           # (N, n) signal-major
+    D = torch.from_numpy(Dh).to(DEV)
+    G = torch.empty((K, K), device=DEV)
+    _native.check(lib.lys_gram(D.data_ptr(), K, n, K, G.data_ptr(), None))
+    wsb = lib.lys_bomp_workspace_bytes(n, K, N, k)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    outs = []
+    for zss in (K, K + 64, 0):
+        idx = torch.full((N, k), -9, dtype=torch.int32, device=DEV); val = torch.full((N, k), 9.0, device=DEV)
+        Z = torch.full((N, max(zss, 1)), 7.0, device=DEV) if zss else None
+        _native.check(lib.lys_bomp_encode(X.data_ptr(), 1, n, D.data_ptr(), K, G.data_ptr(), n, K, N, k,
+                                          idx.data_ptr(), val.data_ptr(), None, Z.data_ptr() if zss else None, 1, max(zss, K),
+                                          ws.data_ptr(), wsb, None))
+        torch.cuda.synchronize()
+        outs.append((idx.cpu().numpy(), val.cpu().numpy(), None if Z is None else Z.cpu().numpy()))
+    for o in outs[1:]:
+        assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1])
+    for o in outs[:2]:
+        Zd = o[2][:, :K]
+        ref = np.zeros((N, K), dtype=np.float32)
+        ref[np.arange(N)[:, None], o[0]] = o[1]
+        assert np.array_equal(Zd, ref)
+        if o[2].shape[1] > K:
+            assert np.all(o[2][:, K:] == 7.0)                           # padding columns untouched
