@@ -159,7 +159,7 @@ __device__ __forceinline__ int argmax_finish_r(const ArgmaxStateR& am)
 #define LYS_ZGROUPS 1
 #endif
 #ifndef LYS_ZSLEEP
-#define LYS_ZSLEEP 2000
+#define LYS_ZSLEEP 0
 #endif
 #ifndef LYS_ZHINT
 #define LYS_ZHINT 1
@@ -468,6 +468,9 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                     if (a0 >= 0) zf[o0 + a0] = 0.f;
                     if (a1 >= 0) zf[o1 + a1] = 0.f;
                     __syncwarp();
+#if LYS_ZSLEEP > 0
+                    __nanosleep(LYS_ZSLEEP);                                   // spread the tile's 512 KB over its lifetime
+#endif
                     a0 = na0; v0 = nv0; o0 = no0; a1 = na1; v1 = nv1; o1 = no1;
                 }
             }
