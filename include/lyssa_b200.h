@@ -175,6 +175,21 @@ LYS_API size_t lys_odl_update_workspace_bytes(int n, int K);
 LYS_API int lys_odl_update_dict(float* D, int64_t ldd, const float* A, const float* B, int n, int K,
                         int non_neg, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- ScSPM spatial-pyramid pooling from sparse codes (first "next" row) -----
+ * replaces the per-image loop of sc_spm_extractor.encode, lyssa/feature_extract/spatial_pyramid.py:45-97,
+ * with the pooling operators of lyssa/feature_extract/pooling.py:4-26, for a batch of images:
+ * patch p belongs to image patch_img[p], its top-left pixel is (patch_pos[2p], patch_pos[2p+1]) = (row, col)
+ * (:60-63), img_hw[2i], img_hw[2i+1] = height, width of image i, `levels` is a HOST array (e.g. {1,2,4}).
+ * F (n_imgs, total_cells*K) row-major receives, per image, the (cell, atom) features in the reference's order
+ * (level-major, cell-major, atom-minor, :94-96).  pooling: 0 = max |z| (sc_max_pooling), 1 = sum, 2 = average
+ * over the patches of the cell; l2_normalize != 0 applies x/(||x||+eps) per non-empty cell
+ * (feature_extract/preproc.py:8-15).  cell_count (n_imgs*total_cells int32) is scratch / returns the patches per cell. */
+LYS_API int lys_spm_total_cells(const int32_t* levels, int n_levels);
+LYS_API int lys_spm_pool(const int32_t* idx, const float* val, int64_t N, int k, int K,
+                         const int32_t* patch_img, const float* patch_pos, float patch_size,
+                         const int32_t* img_hw, int n_imgs, const int32_t* levels, int n_levels,
+                         int pooling, int l2_normalize, float* F, int32_t* cell_count, void* stream);
+
 /* ---- multi-GPU: peer-mapped exchange buffers for the sweep's per-atom all-reduce ---------
  * One process per GPU.  Each rank creates a comm (allocates its exchange buffer), exports
  * a 64-byte handle, the host (torch.distributed) all-gathers the handles, and every rank

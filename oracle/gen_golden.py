@@ -158,6 +158,24 @@ def main():
     Di, unused = ref.init_dictionary(Xi.astype(float), 12, method="data", return_unused_data=True)
     np.savez_compressed(os.path.join(OUT, "init_dict.npz"), X=Xi, D=Di, unused=np.array(unused, dtype=np.int32), seed=33)
 
+
+
+    # ---- ScSPM pooling: the reference's sc_spm_extractor on 5 small synthetic images,
+    # grid descriptors (stand-in for dense SIFT), K=96, k=3, levels (1,2,4), three pooling operators
+    imgs = lo.synthetic_images(5, seed=3)
+    fe = lo.grid_descriptor_extractor(step_size=4, patch_size=8)
+    D = lo.synthetic_dictionary(96, 64, seed=5)
+    out = {"D": D, "k": 3, "levels": np.array([1, 2, 4]), "step_size": 4, "patch_size": 8, "n_imgs": len(imgs)}
+    for i, im in enumerate(imgs):
+        out["img%d" % i] = im
+    for name, op, nrm in (("absmax_l2", ref.sc_max_pooling(), True), ("sum", ref.sum_pooling(), False),
+                          ("avg_l2", ref.average_pooling(), True)):
+        with rl.quiet():
+            enc = ref.sparse_encoder(algorithm="bomp", params={"n_nonzero_coefs": 3}, verbose=False)
+            out["Z_" + name] = ref.sc_spm_extractor(feature_extractor=fe, levels=(1, 2, 4), sparse_coder=enc, pooling_operator=op,
+                                                    normalizer=ref.l2_normalizer() if nrm else None).encode(imgs, D.astype(float))
+    np.savez_compressed(os.path.join(OUT, "spm.npz"), **out)
+
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

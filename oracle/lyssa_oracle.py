@@ -350,6 +350,116 @@ def online_dict_learn(X, n_atoms, sparse_coder=None, batch_size=None, A=None, B=
 
 
 # ------------------------------------------------------------------------- synthetic data
+# ----------------------------------------------------------------------------- ScSPM pooling
+class sc_max_pooling(object):
+    """lyssa/feature_extract/pooling.py:4-7"""
+    def __call__(self, Z):
+        return np.max(np.abs(Z), axis=1)
+
+
+class sum_pooling(object):
+    """lyssa/feature_extract/pooling.py:16-19"""
+    def __call__(self, Z):
+        return np.sum(Z, axis=1)
+
+
+class average_pooling(object):
+    """lyssa/feature_extract/pooling.py:22-26"""
+    def __call__(self, Z):
+        return np.sum(Z, axis=1) / float(Z.shape[1])
+
+
+class l2_normalizer(object):
+    """lyssa/feature_extract/preproc.py:8-15 (1-D case)"""
+    def __call__(self, Z):
+        return normalize(Z)
+
+
+class sc_spm_extractor(object):
+    """Restatement of lyssa/feature_extract/spatial_pyramid.py:34-97 (per image: descriptors + positions
+    from the feature extractor, sparse codes, cell membership per pyramid level, pool, normalise)."""
+
+    def __init__(self, feature_extractor=None, levels=(1, 2, 4), sparse_coder=None, pooling_operator=None, normalizer=None):
+        self.feature_extractor = feature_extractor
+        self.levels = levels
+        self.sparse_coder = sparse_coder
+        self.pooling_operator = pooling_operator
+        self.normalizer = normalizer
+
+    def encode(self, imgs, dictionary):
+        psize = self.feature_extractor.patch_size                       # :47
+        n_imgs = len(imgs)
+        n_atoms = dictionary.shape[1]
+        cells = np.array(self.levels) ** 2                              # :50
+        n_features = np.sum(cells) * n_atoms
+        Z = np.zeros((n_features, n_imgs))
+        for k in range(n_imgs):                                         # :54
+            img = imgs[k]
+            desc, pos = self.feature_extractor.extract(img)             # :57
+            py = pos[:, 0]
+            px = pos[:, 1]
+            cy = py + float(psize) / 2 - 0.5                            # :62-63
+            cx = px + float(psize) / 2 - 0.5
+            coded_patches = self.sparse_coder.encode(desc, dictionary)  # :66
+            n_atoms = coded_patches.shape[0]
+            n_total_cells = np.sum(cells)
+            imsize = img.shape
+            poolpatches = np.zeros((n_total_cells, n_atoms))            # :74
+            cnt = 0
+            for (i, lev) in enumerate(self.levels):                     # :77
+                wunit = float(imsize[1]) / lev
+                hunit = float(imsize[0]) / lev
+                binidx = np.floor(cy / hunit) * lev + np.floor(cx / wunit)      # :83
+                for j in range(cells[i]):
+                    pidx = np.nonzero(binidx == j)[0]
+                    if len(pidx) > 0:
+                        poolpatches[cnt, :] = self.pooling_operator(coded_patches[:, pidx])   # :91
+                        if self.normalizer is not None:
+                            poolpatches[cnt, :] = self.normalizer(poolpatches[cnt, :])
+                    cnt += 1
+            Z[:, k] = poolpatches.flatten()                             # :96
+        return Z
+
+
+class grid_descriptor_extractor(object):
+    """Synthetic stand-in for the reference's dsift_extractor (spatial_pyramid.py:9-20): descriptors on a
+    regular grid of patch_size x patch_size patches (top-left positions, step_size apart), here simply the
+    mean-removed pixels of the patch.  Returns (desc (n, P), pos (P, 2)) like ``extract`` does."""
+
+    def __init__(self, step_size=4, patch_size=8):
+        self.step_size = step_size
+        self.patch_size = patch_size
+
+    def extract(self, img):
+        img = np.asarray(img, dtype=np.float64)
+        H, W = img.shape
+        ps, st = self.patch_size, self.step_size
+        rows = np.arange(0, H - ps + 1, st)
+        cols = np.arange(0, W - ps + 1, st)
+        desc = np.empty((ps * ps, len(rows) * len(cols)))
+        pos = np.empty((len(rows) * len(cols), 2))
+        c = 0
+        for r in rows:
+            for q in cols:
+                patch = img[r:r + ps, q:q + ps].reshape(-1)
+                desc[:, c] = patch - patch.mean()
+                pos[c] = (r, q)
+                c += 1
+        return desc, pos
+
+
+def synthetic_images(n_imgs, seed=0, sizes=((48, 64), (40, 40), (33, 57))):
+    """seeded smooth-noise grayscale images of a few different sizes (SURVEY.md section 8d, cfg5 in miniature)"""
+    rng = np.random.default_rng(seed)
+    imgs = []
+    for i in range(n_imgs):
+        H, W = sizes[i % len(sizes)]
+        a = rng.random((H + 4, W + 4))
+        a = (a[:-4, :-4] + a[2:-2, 2:-2] + a[4:, 4:] + a[:-4, 4:] + a[4:, :-4]) / 5.0
+        imgs.append(np.ascontiguousarray(a, dtype=np.float64))
+    return imgs
+
+
 def synthetic_patches(n_signals, n_features=64, seed=0):
     """uniform [0,1) pixels, per-patch mean removed; returns float32 (n, N)
     'datapoints in columns' as a transposed view of signal-major storage."""

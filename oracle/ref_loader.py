@@ -197,7 +197,22 @@ def load():
     gd_ns = dict(od_ns)
     _load_defs("lyssa/dict_learning/gradient_descent.py", gd_ns)
 
+    # ScSPM pooling: spatial_pyramid.py needs only numpy once its lyssa.* imports
+    # (DsiftExtractor, grid_patches, run_parallel, get_mmap: producers / orchestration) are dropped
+    sp_ns = dict(base)
+    sp_ns["run_parallel"] = utils_ns["run_parallel"]
+    _load_defs("lyssa/feature_extract/spatial_pyramid.py", sp_ns)
+    pool_ns = dict(base)
+    _load_defs("lyssa/feature_extract/pooling.py", pool_ns)
+    pre_ns = dict(base)
+    _load_defs("lyssa/feature_extract/preproc.py", pre_ns)
+
     ref = _Ref()
+    ref.sc_spm_extractor = sp_ns["sc_spm_extractor"]
+    ref.sc_max_pooling = pool_ns["sc_max_pooling"]
+    ref.sum_pooling = pool_ns["sum_pooling"]
+    ref.average_pooling = pool_ns["average_pooling"]
+    ref.l2_normalizer = pre_ns["l2_normalizer"]
     ref.fast_dot = rmath.fast_dot
     ref.norm = rmath.norm
     ref.normalize = rmath.normalize

@@ -1,0 +1,61 @@
+"""GPU parity of the ScSPM pooling path (first "next" row) through the
+reference-facing class: golden features from the live reference and seeded cases vs the oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from oracle import lyssa_oracle as lo  # noqa: E402
+from lyssandra_b200.sparse_coding import sparse_encoder  # noqa: E402
+from lyssandra_b200.feature_extract import (sc_spm_extractor, sc_max_pooling, sum_pooling, average_pooling,  # noqa: E402
+                                            max_pooling, l2_normalizer)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _run(imgs, fe, D, k, levels, op, nrm):
+    enc = sparse_encoder(algorithm="bomp", params={"n_nonzero_coefs": k}, verbose=False)
+    ex = sc_spm_extractor(feature_extractor=fe, levels=levels, sparse_coder=enc, pooling_operator=op,
+                          normalizer=l2_normalizer() if nrm else None)
+    Z = ex.encode(imgs, torch.from_numpy(np.ascontiguousarray(D, dtype=np.float32)).to(DEV))
+    return Z.cpu().numpy().astype(np.float64)
+
+
+def test_spm_golden(golden):
+    g = golden("spm")
+    imgs = [g["img%d" % i] for i in range(int(g["n_imgs"]))]
+    fe = lo.grid_descriptor_extractor(step_size=int(g["step_size"]), patch_size=int(g["patch_size"]))
+    levels = tuple(int(v) for v in g["levels"])
+    for name, op, nrm in (("absmax_l2", sc_max_pooling(), True), ("sum", sum_pooling(), False), ("avg_l2", average_pooling(), True)):
+        Z = _run(imgs, fe, g["D"], int(g["k"]), levels, op, nrm)
+        ref = g["Z_" + name]
+        assert Z.shape == ref.shape
+        assert np.array_equal(Z != 0, ref != 0), name                      # same cells / atoms populated
+        assert np.max(np.abs(Z - ref)) <= 2e-5 * np.max(np.abs(ref)), (name, np.max(np.abs(Z - ref)))
+
+
+@pytest.mark.parametrize("levels,K,k", [((1, 2, 4), 256, 5), ((1, 3), 1024, 5), ((2,), 100, 2)])
+def test_spm_seeded_vs_oracle(levels, K, k):
+    imgs = lo.synthetic_images(7, seed=21, sizes=((64, 48), (50, 50), (37, 71)))
+    fe = lo.grid_descriptor_extractor(step_size=3, patch_size=8)
+    D = lo.synthetic_dictionary(K, 64, seed=22)
+    enc_o = lo.sparse_encoder("bomp", {"n_nonzero_coefs": k}, verbose=False)
+    Zo = lo.sc_spm_extractor(feature_extractor=fe, levels=levels, sparse_coder=enc_o, pooling_operator=lo.sc_max_pooling(),
+                             normalizer=None).encode(imgs, D.astype(np.float64))
+    Z = _run(imgs, fe, D, k, levels, sc_max_pooling(), False)
+    assert Z.shape == (sum(l * l for l in levels) * K, len(imgs))
+    # max |z| pooling only moves when a support differs: near-tie columns may change single entries
+    bad = np.abs(Z - Zo) > 2e-5 * np.max(np.abs(Zo))
+    assert bad.mean() < 1e-3, bad.mean()
+
+
+def test_spm_errors():
+    imgs = lo.synthetic_images(1, seed=1)
+    fe = lo.grid_descriptor_extractor()
+    D = lo.synthetic_dictionary(256, 64, seed=2)
+    with pytest.raises(NotImplementedError):
+        _run(imgs, fe, D, 3, (1, 2), max_pooling(), False)

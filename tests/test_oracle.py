@@ -147,3 +147,39 @@ def test_oracle_matches_live_reference():
     np.random.seed(5)
     D2, A2, B2 = lo.online_dict_learn(X, 40, sparse_coder=lo.sparse_encoder("bomp", {"n_nonzero_coefs": 3}), batch_size=64, n_epochs=2)
     assert np.max(np.abs(D1 - D2)) <= 1e-14 and np.max(np.abs(A1 - A2)) <= 1e-13 and np.max(np.abs(B1 - B2)) <= 1e-13
+
+
+def _spm_inputs(g):
+    imgs = [g["img%d" % i] for i in range(int(g["n_imgs"]))]
+    fe = lo.grid_descriptor_extractor(step_size=int(g["step_size"]), patch_size=int(g["patch_size"]))
+    return imgs, fe, g["D"].astype(np.float64), int(g["k"]), tuple(int(v) for v in g["levels"])
+
+
+def test_spm_oracle_matches_golden(golden):
+    """ScSPM pooling: the restatement of sc_spm_extractor.encode reproduces the
+    live reference's features (tests/golden/spm.npz, made by oracle/gen_golden.py)."""
+    g = golden("spm")
+    imgs, fe, D, k, levels = _spm_inputs(g)
+    enc = lo.sparse_encoder("bomp", {"n_nonzero_coefs": k}, verbose=False)
+    for name, op, nrm in (("absmax_l2", lo.sc_max_pooling(), True), ("sum", lo.sum_pooling(), False),
+                          ("avg_l2", lo.average_pooling(), True)):
+        Z = lo.sc_spm_extractor(feature_extractor=fe, levels=levels, sparse_coder=enc, pooling_operator=op,
+                                normalizer=lo.l2_normalizer() if nrm else None).encode(imgs, D)
+        assert Z.shape == g["Z_" + name].shape == (21 * D.shape[1], len(imgs))
+        assert np.max(np.abs(Z - g["Z_" + name])) < 1e-12, name
+
+
+@pytest.mark.skipif(not rl.available(), reason="reference tree not present (GPU box)")
+def test_spm_oracle_matches_live_reference():
+    ref = rl.load()
+    imgs = lo.synthetic_images(4, seed=11)
+    fe = lo.grid_descriptor_extractor(step_size=5, patch_size=8)
+    D = lo.synthetic_dictionary(80, 64, seed=12).astype(np.float64)
+    with rl.quiet():
+        enc_r = ref.sparse_encoder(algorithm="bomp", params={"n_nonzero_coefs": 4}, verbose=False)
+        Zr = ref.sc_spm_extractor(feature_extractor=fe, levels=(1, 2, 3), sparse_coder=enc_r, pooling_operator=ref.sc_max_pooling(),
+                                  normalizer=None).encode(imgs, D)
+    enc_o = lo.sparse_encoder("bomp", {"n_nonzero_coefs": 4}, verbose=False)
+    Zo = lo.sc_spm_extractor(feature_extractor=fe, levels=(1, 2, 3), sparse_coder=enc_o, pooling_operator=lo.sc_max_pooling(),
+                             normalizer=None).encode(imgs, D)
+    assert np.array_equal(Zr, Zo)
