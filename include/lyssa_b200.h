@@ -190,6 +190,20 @@ LYS_API int lys_spm_pool(const int32_t* idx, const float* val, int64_t N, int k,
                          const int32_t* img_hw, int n_imgs, const int32_t* levels, int n_levels,
                          int pooling, int l2_normalize, float* F, int32_t* cell_count, void* stream);
 
+/* ---- dense SIFT descriptors (second "next" row) -------------------------------------
+ * replaces DsiftExtractor.process_image / extract_sift_patches / normalize_sift,
+ * lyssa/feature_extract/dsift.py:75-162, for one grayscale image (H, W) float32 on the device.
+ * lys_dsift_grid: the sampling grid of :101-109 (n_h x n_w patches, offsets of the first patch).
+ * gh25 / gw25: the 5x5 Gaussian-derivative kernels of gen_dgauss (:23-35) and bin_weights (4, patch_size):
+ * the separable factor of the bilinear weight matrix (:57-73) — HOST arrays (a few dozen floats the host side
+ * computes with the reference's own formulas).  desc (n_h*n_w, 128) row-major, descriptor element
+ * angle*16 + bin as in :139-141; pos (n_h*n_w, 2) = top-left (row, col) of every patch, patch order of :107-109. */
+LYS_API size_t lys_dsift_workspace_bytes(int H, int W);
+LYS_API int lys_dsift_grid(int H, int W, int grid_spacing, int patch_size, int* n_h, int* n_w, int* off_h, int* off_w);
+LYS_API int lys_dsift(const float* img, int64_t row_stride, int H, int W, int grid_spacing, int patch_size,
+                      float nrml_thres, float sift_thres, const float* gh25, const float* gw25, const float* bin_weights,
+                      float* desc, float* pos, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- multi-GPU: peer-mapped exchange buffers for the sweep's per-atom all-reduce ---------
  * One process per GPU.  Each rank creates a comm (allocates its exchange buffer), exports
  * a 64-byte handle, the host (torch.distributed) all-gathers the handles, and every rank

@@ -24,6 +24,19 @@ from .pooling import _pool_op, sc_max_pooling
 from .preproc import l2_normalizer
 
 
+class dsift_extractor(object):
+    """lyssa/feature_extract/spatial_pyramid.py:9-20: dense SIFT descriptors (128, P) + top-left positions (P, 2)"""
+
+    def __init__(self, step_size=None, patch_size=None):
+        from .dsift import DsiftExtractor
+        self.patch_size = patch_size
+        self.extractor = DsiftExtractor(grid_spacing=step_size, patch_size=patch_size)
+
+    def extract(self, img):
+        dsift_patches, pos = self.extractor.process_image(img, positionNormalize=False)
+        return dsift_patches.t(), pos.t()
+
+
 def spm_pool(codes, patch_img, patch_pos, patch_size, img_hw, levels=(1, 2, 4), pooling_operator=None, normalizer=None):
     """Pool sparse codes over the spatial pyramid of every image.
 

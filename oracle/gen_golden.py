@@ -176,6 +176,15 @@ def main():
                                                     normalizer=ref.l2_normalizer() if nrm else None).encode(imgs, D.astype(float))
     np.savez_compressed(os.path.join(OUT, "spm.npz"), **out)
 
+    # ---- dense SIFT: the reference's DsiftExtractor on one 60x75 synthetic image
+    img = lo.synthetic_images(1, seed=7, sizes=((60, 75),))[0] * 255.0
+    out = {"img": img}
+    for gs, ps in ((6, 16), (4, 8)):
+        f, p = ref.DsiftExtractor(grid_spacing=gs, patch_size=ps).process_image(img)
+        out["feat_%d_%d" % (gs, ps)] = f
+        out["pos_%d_%d" % (gs, ps)] = p
+    np.savez_compressed(os.path.join(OUT, "dsift.npz"), **out)
+
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

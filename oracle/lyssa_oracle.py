@@ -421,6 +421,113 @@ class sc_spm_extractor(object):
         return Z
 
 
+class DsiftExtractor(object):
+    """Restatement of lyssa/feature_extract/dsift.py:16-162 (dense SIFT after Lazebnik); the only edit is
+    ``np.int`` -> ``int`` (:27, removed from NumPy 1.24)."""
+    n_angles = 8
+    n_bins = 4
+    alpha = 9.0
+
+    @staticmethod
+    def gen_dgauss(sigma):                                              # :23-35
+        fwid = int(2 * np.ceil(sigma))
+        G = np.array(range(-fwid, fwid + 1)) ** 2
+        G = G.reshape((G.size, 1)) + G
+        G = np.exp(- G / 2.0 / sigma / sigma)
+        G /= np.sum(G)
+        GH, GW = np.gradient(G)
+        GH *= 2.0 / np.sum(np.abs(GH))
+        GW *= 2.0 / np.sum(np.abs(GW))
+        return GH, GW
+
+    def __init__(self, grid_spacing=None, patch_size=None, nrml_thres=1.0, sigma_edge=0.8, sift_thres=0.2):
+        n_bins = self.n_bins
+        self.gs = grid_spacing
+        self.ps = patch_size
+        self.nrml_thres = nrml_thres
+        self.sigma = sigma_edge
+        self.sift_thres = sift_thres
+        sample_res = self.ps / np.double(n_bins)                        # :57-73
+        sample_p = np.array(range(self.ps))
+        sample_ph, sample_pw = np.meshgrid(sample_p, sample_p)
+        sample_ph = sample_ph.reshape(-1)
+        sample_pw = sample_pw.reshape(-1)
+        bincenter = np.array(range(1, n_bins * 2, 2)) / 2.0 / n_bins * self.ps - 0.5
+        bincenter_h, bincenter_w = np.meshgrid(bincenter, bincenter)
+        bincenter_h = bincenter_h.reshape((-1, 1))
+        bincenter_w = bincenter_w.reshape((-1, 1))
+        weights_h = abs(sample_ph - bincenter_h) / sample_res
+        weights_w = abs(sample_pw - bincenter_w) / sample_res
+        weights_h = (1 - weights_h) * (weights_h <= 1)
+        weights_w = (1 - weights_w) * (weights_w <= 1)
+        self.weights = weights_h * weights_w
+
+    def process_image(self, image, positionNormalize=False):            # :75-118
+        from math import floor
+        image = image.astype(np.double)
+        if image.ndim == 3:
+            image = np.mean(image, axis=2)
+        h, w = image.shape
+        gs, ps = self.gs, self.ps
+        rem_h = np.mod(h - ps, gs)
+        rem_w = np.mod(w - ps, gs)
+        offset_h = int(floor(rem_h / 2.))
+        offset_w = int(floor(rem_w / 2.))
+        grid_h, grid_w = np.meshgrid(range(offset_h, h - ps + 1, gs), range(offset_w, w - ps + 1, gs))
+        grid_h = grid_h.flatten()
+        grid_w = grid_w.flatten()
+        feat_arr = self.extract_sift_patches(image, grid_h, grid_w)
+        if positionNormalize:
+            positions = np.vstack((grid_h / np.double(h), grid_w / np.double(w)))
+        else:
+            positions = np.vstack((grid_h, grid_w))
+        return feat_arr, positions
+
+    def extract_sift_patches(self, image, grid_h, grid_w):              # :120-144
+        from scipy import signal
+        n_angles, n_samples = self.n_angles, self.n_bins ** 2
+        angles = np.array(range(n_angles)) * 2.0 * np.pi / n_angles
+        h, w = image.shape
+        n_patches = grid_h.size
+        feat_arr = np.zeros((n_patches, n_samples * n_angles))
+        gh, gw = self.gen_dgauss(self.sigma)
+        ih = signal.convolve2d(image, gh, mode='same')
+        iw = signal.convolve2d(image, gw, mode='same')
+        i_mag = np.sqrt(ih ** 2 + iw ** 2)
+        i_theta = np.arctan2(ih, iw)
+        i_orient = np.zeros((n_angles, h, w))
+        for i in range(n_angles):
+            i_orient[i] = i_mag * np.maximum(np.cos(i_theta - angles[i]) ** self.alpha, 0)
+        for i in range(n_patches):
+            curr_feature = np.zeros((n_angles, n_samples))
+            for j in range(n_angles):
+                curr_feature[j] = np.dot(self.weights, i_orient[j, grid_h[i]:grid_h[i] + self.ps,
+                                                      grid_w[i]:grid_w[i] + self.ps].flatten())
+            feat_arr[i] = curr_feature.flatten()
+        return self.normalize_sift(feat_arr)
+
+    def normalize_sift(self, feat_arr):                                 # :146-162
+        siftlen = np.sqrt(np.sum(feat_arr ** 2, axis=1))
+        hcontrast = (siftlen >= self.nrml_thres)
+        siftlen[siftlen < self.nrml_thres] = self.nrml_thres
+        feat_arr /= siftlen.reshape((siftlen.size, 1))
+        feat_arr[feat_arr > self.sift_thres] = self.sift_thres
+        feat_arr[hcontrast] /= np.sqrt(np.sum(feat_arr[hcontrast] ** 2, axis=1)).reshape((feat_arr[hcontrast].shape[0], 1))
+        return feat_arr
+
+
+class dsift_extractor(object):
+    """lyssa/feature_extract/spatial_pyramid.py:9-20"""
+
+    def __init__(self, step_size=None, patch_size=None):
+        self.patch_size = patch_size
+        self.extractor = DsiftExtractor(grid_spacing=step_size, patch_size=patch_size)
+
+    def extract(self, img):
+        dsift_patches, pos = self.extractor.process_image(img, positionNormalize=False)
+        return dsift_patches.T, pos.T
+
+
 class grid_descriptor_extractor(object):
     """Synthetic stand-in for the reference's dsift_extractor (spatial_pyramid.py:9-20): descriptors on a
     regular grid of patch_size x patch_size patches (top-left positions, step_size apart), here simply the

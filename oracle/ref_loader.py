@@ -57,13 +57,16 @@ def _py3_text(src: str, rel: str) -> str:
         # :332 inside batch_omp only (the j == 1 branch); `w = g` appears once in that form
         text, n = re.subn(r"^(\s+)w = g$", r"\1w = g[0]", text, flags=re.M)
         assert n == 1, "expected exactly one `w = g` line in batch_omp"
+    if rel.endswith("dsift.py"):
+        text, n = re.subn(r"np\.int\(", "int(", text)          # :27, np.int was removed in NumPy 1.24
+        assert n == 1
     if rel.endswith("ksvd.py"):
         text, n = re.subn(r"if init_dict == 'data':", "if isinstance(init_dict, str) and init_dict == 'data':", text)
         assert n == 1
     return text
 
 
-_SAFE_IMPORT_ROOTS = {"numpy", "scipy", "functools", "itertools", "sys", "time", "warnings", "__future__", "os"}
+_SAFE_IMPORT_ROOTS = {"numpy", "scipy", "functools", "itertools", "sys", "time", "warnings", "__future__", "os", "math"}
 
 
 def _load_defs(rel: str, ns: dict) -> dict:
@@ -207,7 +210,15 @@ def load():
     pre_ns = dict(base)
     _load_defs("lyssa/feature_extract/preproc.py", pre_ns)
 
+    ds_ns = dict(base)
+    _load_defs("lyssa/feature_extract/dsift.py", ds_ns)
+    # module-level constants of dsift.py that are not plain literals (:17-21)
+    ds_ns.update(n_angles=8, n_bins=4, n_samples=16, alpha=9.0, angles=np.array(range(8)) * 2.0 * np.pi / 8)
+    sp_ns["DsiftExtractor"] = ds_ns["DsiftExtractor"]
+
     ref = _Ref()
+    ref.DsiftExtractor = ds_ns["DsiftExtractor"]
+    ref.dsift_extractor = sp_ns["dsift_extractor"]
     ref.sc_spm_extractor = sp_ns["sc_spm_extractor"]
     ref.sc_max_pooling = pool_ns["sc_max_pooling"]
     ref.sum_pooling = pool_ns["sum_pooling"]

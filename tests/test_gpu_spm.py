@@ -59,3 +59,31 @@ def test_spm_errors():
     D = lo.synthetic_dictionary(256, 64, seed=2)
     with pytest.raises(NotImplementedError):
         _run(imgs, fe, D, 3, (1, 2), max_pooling(), False)
+
+
+# ---------------------------------------------------------------- dense SIFT producer
+def test_dsift_golden(golden):
+    from lyssandra_b200.feature_extract import DsiftExtractor
+    g = golden("dsift")
+    for gs, ps in ((6, 16), (4, 8)):
+        f, p = DsiftExtractor(grid_spacing=gs, patch_size=ps).process_image(g["img"])
+        ref_f, ref_p = g["feat_%d_%d" % (gs, ps)], g["pos_%d_%d" % (gs, ps)]
+        assert tuple(f.shape) == ref_f.shape and np.array_equal(p.cpu().numpy(), ref_p)
+        err = np.max(np.abs(f.cpu().numpy().astype(np.float64) - ref_f))
+        assert err <= 2e-5, err                      # descriptors are unit-norm, entries <= 0.2 .. 0.5; float32 pipeline
+
+
+def test_dsift_seeded_and_scspm_pipeline():
+    """images -> dense SIFT (device) -> Batch-OMP -> pyramid pooling, vs the oracle pipeline in float64"""
+    from lyssandra_b200.feature_extract import dsift_extractor
+    imgs = [im * 255.0 for im in lo.synthetic_images(4, seed=31, sizes=((64, 80), (72, 72)))]
+    K, k = 256, 4
+    D = lo.synthetic_dictionary(K, 128, seed=32)
+    enc_o = lo.sparse_encoder("bomp", {"n_nonzero_coefs": k}, verbose=False)
+    Zo = lo.sc_spm_extractor(feature_extractor=lo.dsift_extractor(step_size=6, patch_size=16), levels=(1, 2, 4),
+                             sparse_coder=enc_o, pooling_operator=lo.sc_max_pooling(),
+                             normalizer=lo.l2_normalizer()).encode(imgs, D.astype(np.float64))
+    Z = _run(imgs, dsift_extractor(step_size=6, patch_size=16), D, k, (1, 2, 4), sc_max_pooling(), True)
+    assert Z.shape == Zo.shape
+    bad = np.abs(Z - Zo) > 1e-4 * np.max(np.abs(Zo))
+    assert bad.mean() < 5e-3, bad.mean()             # a flipped near-tie support moves a few pooled entries

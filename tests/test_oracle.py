@@ -183,3 +183,21 @@ def test_spm_oracle_matches_live_reference():
     Zo = lo.sc_spm_extractor(feature_extractor=fe, levels=(1, 2, 3), sparse_coder=enc_o, pooling_operator=lo.sc_max_pooling(),
                              normalizer=None).encode(imgs, D)
     assert np.array_equal(Zr, Zo)
+
+
+def test_dsift_oracle_matches_golden(golden):
+    """dense SIFT: restated DsiftExtractor vs the live reference's descriptors"""
+    g = golden("dsift")
+    for gs, ps in ((6, 16), (4, 8)):
+        f, p = lo.DsiftExtractor(grid_spacing=gs, patch_size=ps).process_image(g["img"])
+        assert np.array_equal(p, g["pos_%d_%d" % (gs, ps)])
+        assert np.max(np.abs(f - g["feat_%d_%d" % (gs, ps)])) < 1e-12
+
+
+@pytest.mark.skipif(not rl.available(), reason="reference tree not present (GPU box)")
+def test_dsift_oracle_matches_live_reference():
+    ref = rl.load()
+    img = lo.synthetic_images(1, seed=19, sizes=((45, 38),))[0] * 200.0
+    fr, pr = ref.DsiftExtractor(grid_spacing=5, patch_size=12).process_image(img)
+    fo, po = lo.DsiftExtractor(grid_spacing=5, patch_size=12).process_image(img)
+    assert np.array_equal(fr, fo) and np.array_equal(pr, po)
