@@ -127,6 +127,11 @@ LYS_API int lys_residual(const float* X, int64_t x_feat_stride, int64_t x_sig_st
                  int n, int K, int64_t N, int k, float* R, double* err,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* ||A||_F^2 of a contiguous, 16-byte aligned float array into ONE device double (deterministic).  After
+ * lys_approx_ksvd_sweep the residual R it maintains IS X - D Z, so this replaces the reference's second dense
+ * recomputation `error = approx_error(D, Z, X)` (ksvd.py:220) with one pass over R.  workspace: 32 KB. */
+LYS_API int lys_frobenius2(const float* A, int64_t count, double* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- K6: users-of-atom index (CSR by atom) ---------------------------------------------
  * replaces the per-atom scan `omega_k = X[k, :] != 0`, ksvd.py:111.
  * rowptr (K+1) int32; entries (N*k) int32, entry = i*k + slot, ascending inside each atom

@@ -43,6 +43,7 @@ SIGNATURES = {
     "lys_odl_accumulate": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_f, c_vp, c_vp, c_vp]),
     "lys_odl_update_workspace_bytes": (c_sz, [c_int, c_int]),
     "lys_odl_update_dict": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_sz, c_vp]),
+    "lys_frobenius2": (c_int, [c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "lys_spm_total_cells": (c_int, [c_vp, c_int]),
     "lys_spm_pool": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, ctypes.c_float, c_vp, c_int, c_vp, c_int,
                              c_int, c_int, c_vp, c_vp, c_vp]),

@@ -134,6 +134,26 @@ __global__ void sum_partials_kernel(const double* __restrict__ partial, int coun
     if (threadIdx.x == 0) *out = s;
 }
 
+// ||A||_F^2 of a contiguous array: per-block partial in double, fixed-order final sum (deterministic)
+__global__ void __launch_bounds__(256)
+frob2_kernel(const float* __restrict__ A, int64_t count, double* __restrict__ partial)
+{
+    __shared__ double wsum[8];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    double s = 0.0;
+    const int64_t n4 = count / 4;
+    const float4* A4 = reinterpret_cast<const float4*>(A);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + t; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(A4 + i);
+        s += (double)(v.x * v.x + v.y * v.y) + (double)(v.z * v.z + v.w * v.w);
+    }
+    if (blockIdx.x == 0 && t < (int)(count - n4 * 4)) { const float v = A[n4 * 4 + t]; s += (double)v * v; }
+    s = warp_sum(s);
+    if (lane == 0) wsum[warp] = s;
+    __syncthreads();
+    if (t == 0) { double r = 0.0; for (int w = 0; w < 8; ++w) r += wsum[w]; partial[blockIdx.x] = r; }
+}
+
 // --------------------------------------------------------------------------- atom CSR
 constexpr int CSR_WARPS = 4;
 
@@ -299,6 +319,21 @@ extern "C" int lys_residual(const float* X, int64_t xfs, int64_t xss, const floa
         sum_partials_kernel<<<1, 32, 0, stream>>>(partial, grid, err);
         LYS_LAUNCH_CHECK("sum_partials_kernel");
     }
+    return LYS_OK;
+}
+
+extern "C" int lys_frobenius2(const float* A, int64_t count, double* out, void* workspace, size_t workspace_bytes, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LYS_CHECK_ARG(A && out && workspace && count >= 0, "lys_frobenius2: bad argument");
+    LYS_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0, "lys_frobenius2: A must be 16-byte aligned");
+    const int grid = std::min(4096, sm_count() * 8);
+    if (workspace_bytes < sizeof(double) * 4096) { set_error("lys_frobenius2: workspace too small (32 KB)"); return LYS_EWORKSPACE; }
+    double* partial = reinterpret_cast<double*>(workspace);
+    frob2_kernel<<<grid, 256, 0, stream>>>(A, count, partial);
+    LYS_LAUNCH_CHECK("frob2_kernel");
+    sum_partials_kernel<<<1, 32, 0, stream>>>(partial, grid, out);
+    LYS_LAUNCH_CHECK("sum_partials_kernel");
     return LYS_OK;
 }
 

@@ -26,13 +26,20 @@ def approx_ksvd(Y, D, X, n_cycles=1, verbose=True, comm=None):
 
     Y: (n, N) CUDA tensor; D: (n, K) CUDA tensor; X: engine.SparseCodes (the sparse form of
     the reference's dense Z; its ``val`` is refreshed in place, the support never changes)."""
+    D, X, unused_atoms, _ = _approx_ksvd_keep_residual(Y, D, X, n_cycles, comm)
+    return D, X, unused_atoms
+
+
+def _approx_ksvd_keep_residual(Y, D, X, n_cycles=1, comm=None):
+    """approx_ksvd that also hands back the residual the sweep kept current: after the sweep R == Y - D X
+    (ksvd.py:123), so ||R||_F^2 is the reference's approx_error(D, X, Y) (:220) without a second pass over Y."""
     if not isinstance(X, engine.SparseCodes):
         raise TypeError("approx_ksvd takes engine.SparseCodes (use sparse_encoder.encode_sparse)")
     R, _ = engine.residual(Y, D, X, want_residual=True, want_error=False)         # :103
     rowptr, entries = engine.build_atom_csr(X)                                      # :111
     flags = engine.approx_ksvd_sweep(R, D, X, rowptr, entries, n_cycles=n_cycles, comm=comm)   # :105-124
     unused_atoms = torch.nonzero(flags).flatten().cpu().tolist()
-    return D, X, unused_atoms
+    return D, X, unused_atoms, R
 
 
 def ksvd_dict_learn(X, n_atoms, init_dict="data", sparse_coder=None, max_iter=20, non_neg=False,
@@ -88,7 +95,7 @@ def ksvd_dict_learn(X, n_atoms, init_dict="data", sparse_coder=None, max_iter=20
         if verbose:
             torch.cuda.synchronize(dev)
         t1 = time.perf_counter()
-        D, _, unused_atoms = approx_ksvd(Xd, D, codes, n_cycles=n_cycles, comm=comm)            # :186
+        D, _, unused_atoms, R = _approx_ksvd_keep_residual(Xd, D, codes, n_cycles=n_cycles, comm=comm)   # :186
         for slot in unused_atoms:                                                               # :199-207
             if len(unused_data) == 0 or (multi and dist.rank != 0):
                 break
@@ -99,7 +106,10 @@ def ksvd_dict_learn(X, n_atoms, init_dict="data", sparse_coder=None, max_iter=20
             unused_data = np.delete(unused_data, pos)
         if multi and len(unused_atoms) > 0:
             dist.broadcast_(D, src=0)
-        _, err = engine.residual(Xd, D, codes, want_residual=False, want_error=True)            # :220
+        # :220 approx_error(D, Z, X): the atoms replaced above have no users, so the residual the sweep
+        # maintained is still X - D Z
+        err = engine.frobenius2(R)
+        del R
         if multi:
             dist.allreduce_sum_(err)
         error_curr = float(err.item())

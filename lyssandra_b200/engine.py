@@ -196,6 +196,18 @@ def residual(X, D, codes: SparseCodes, want_residual=True, want_error=True):
     return R, err
 
 
+def frobenius2(A):
+    """||A||_F^2 as a 1-element float64 device tensor (one pass, deterministic)."""
+    lib = nat.load()
+    A = A if A.is_contiguous() else A.contiguous()
+    dev = A.device
+    out = torch.zeros((1,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        ws = workspace(dev, 32768, tag="frob")
+        nat.check(lib.lys_frobenius2(_ptr(A), A.numel(), _ptr(out), _ptr(ws), ws.numel(), _stream_ptr(dev)))
+    return out
+
+
 def build_atom_csr(codes: SparseCodes):
     """users-of-atom index: rowptr (K+1), entries (N*k) = i*k + slot (ksvd.py:111)."""
     lib = nat.load()
