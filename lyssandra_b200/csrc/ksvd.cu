@@ -55,6 +55,7 @@ constexpr int RES_WARPS = 8;
 constexpr int RES_TILE = 32;       // signals per tile
 constexpr int MAX_NPL = LYS_MAX_FEATURES / 32;
 
+template <int NPL>
 __global__ void __launch_bounds__(RES_WARPS * 32)
 residual_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss,
                 const float* __restrict__ Dt, const int32_t* __restrict__ idx,
@@ -86,26 +87,37 @@ residual_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss,
         for (int s = warp; s < RES_TILE; s += RES_WARPS) {
             const int64_t i = i0 + s;
             if (i >= N) break;
-            float r[MAX_NPL];
+            float r[NPL];
 #pragma unroll
-            for (int q = 0; q < MAX_NPL; ++q) {
+            for (int q = 0; q < NPL; ++q) {
                 int f = lane + 32 * q;
                 r[q] = (f < n) ? xs[s * ldx + f] : 0.f;
             }
-            for (int j = 0; j < k; ++j) {
-                const int a = idx[i * k + j];
-                if (a < 0) continue;
-                const float z = val[i * k + j];
-                const float* d = Dt + (int64_t)a * n;
+            // the k codes of the signal in one coalesced load (lane j holds code j), broadcast by shuffle; atoms are
+            // fetched four at a time so that their L2 latencies overlap (an absent code reads atom 0 with z = 0)
+            int my_a = 0; float my_z = 0.f;
+            if (lane < k) {
+                const int a = idx[i * k + lane];
+                if (a >= 0) { my_a = a; my_z = val[i * k + lane]; }
+            }
+            for (int j0 = 0; j0 < k; j0 += 4) {
+                float dv[4][NPL], z[4];
 #pragma unroll
-                for (int q = 0; q < MAX_NPL; ++q) {
-                    int f = lane + 32 * q;
-                    if (f < n) r[q] = fmaf(-z, __ldg(d + f), r[q]);
+                for (int u = 0; u < 4; ++u) {
+                    const int a = __shfl_sync(0xffffffffu, my_a, (j0 + u) & 31);
+                    z[u] = (j0 + u < k) ? __shfl_sync(0xffffffffu, my_z, (j0 + u) & 31) : 0.f;
+                    const float* d = Dt + (int64_t)a * n;
+#pragma unroll
+                    for (int q = 0; q < NPL; ++q) { const int f = lane + 32 * q; dv[u][q] = (f < n) ? __ldg(d + f) : 0.f; }
                 }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int q = 0; q < NPL; ++q) r[q] = fmaf(-z[u], dv[u][q], r[q]);
             }
             float sq = 0.f;
 #pragma unroll
-            for (int q = 0; q < MAX_NPL; ++q) {
+            for (int q = 0; q < NPL; ++q) {
                 int f = lane + 32 * q;
                 if (f < n) {
                     if (R) R[i * n + f] = r[q];
@@ -155,7 +167,10 @@ frob2_kernel(const float* __restrict__ A, int64_t count, double* __restrict__ pa
 }
 
 // --------------------------------------------------------------------------- atom CSR
-constexpr int CSR_WARPS = 4;
+constexpr int CSR_WARPS = 16;    // warps per CTA (upper bound; fewer when K * 4 B per warp would not fit in shared memory)
+// Each warp counts / places its own contiguous slice of the codes, so the output order is deterministic; the
+// slices are walked 32 entries at a time with dependent shared-memory updates, i.e. latency-bound: 16 warps per
+// SM instead of 4 hide it (2.0 -> 0.84 ms at cfg3).
 
 __device__ __forceinline__ int csr_atom(const int32_t* idx, const float* val, int64_t e, int64_t E)
 {
@@ -174,7 +189,7 @@ csr_hist_kernel(const int32_t* __restrict__ idx, const float* __restrict__ val, 
     int32_t* h = sh + warp * K;
     for (int c = lane; c < K; c += 32) h[c] = 0;
     __syncwarp();
-    const int64_t gw = (int64_t)blockIdx.x * CSR_WARPS + warp;
+    const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     const int64_t lo = gw * per_warp, hi = min(lo + per_warp, E);
     for (int64_t e = lo + lane; e < hi; e += 32) {
         int a = csr_atom(idx, val, e, E);
@@ -243,7 +258,7 @@ csr_fill_kernel(const int32_t* __restrict__ idx, const float* __restrict__ val, 
     extern __shared__ int32_t sh[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int32_t* base = sh + warp * K;
-    const int64_t gw = (int64_t)blockIdx.x * CSR_WARPS + warp;
+    const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     for (int c = lane; c < K; c += 32) base[c] = rowptr[c] + hist[gw * K + c];
     __syncwarp();
     const int64_t lo = gw * per_warp, hi = min(lo + per_warp, E);
@@ -303,7 +318,7 @@ extern "C" int lys_residual(const float* X, int64_t xfs, int64_t xss, const floa
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     LYS_CHECK_ARG(X && D && idx && val && workspace, "lys_residual: null pointer");
-    LYS_CHECK_ARG(n >= 1 && n <= LYS_MAX_FEATURES && K >= 1 && K <= LYS_MAX_ATOMS && ldd >= K && k >= 1 && N >= 0,
+    LYS_CHECK_ARG(n >= 1 && n <= LYS_MAX_FEATURES && K >= 1 && K <= LYS_MAX_ATOMS && ldd >= K && k >= 1 && k <= LYS_MAX_NONZERO && N >= 0,
                   "lys_residual: bad shape");
     if (workspace_bytes < lys_residual_workspace_bytes(n, K, N)) { set_error("lys_residual: workspace too small"); return LYS_EWORKSPACE; }
     float* Dt = reinterpret_cast<float*>(workspace);
@@ -313,7 +328,10 @@ extern "C" int lys_residual(const float* X, int64_t xfs, int64_t xss, const floa
     int64_t tiles = (N + RES_TILE - 1) / RES_TILE;
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, std::min<int64_t>(4096, (int64_t)sm_count() * 8)));
     size_t smem = sizeof(float) * RES_TILE * (n + 1);
-    residual_kernel<<<grid, RES_WARPS * 32, smem, stream>>>(X, xfs, xss, Dt, idx, val, n, N, k, R, partial);
+    if (n <= 32) residual_kernel<1><<<grid, RES_WARPS * 32, smem, stream>>>(X, xfs, xss, Dt, idx, val, n, N, k, R, partial);
+    else if (n <= 64) residual_kernel<2><<<grid, RES_WARPS * 32, smem, stream>>>(X, xfs, xss, Dt, idx, val, n, N, k, R, partial);
+    else if (n <= 128) residual_kernel<4><<<grid, RES_WARPS * 32, smem, stream>>>(X, xfs, xss, Dt, idx, val, n, N, k, R, partial);
+    else residual_kernel<MAX_NPL><<<grid, RES_WARPS * 32, smem, stream>>>(X, xfs, xss, Dt, idx, val, n, N, k, R, partial);
     LYS_LAUNCH_CHECK("residual_kernel");
     if (err) {
         sum_partials_kernel<<<1, 32, 0, stream>>>(partial, grid, err);
@@ -337,12 +355,13 @@ extern "C" int lys_frobenius2(const float* A, int64_t count, double* out, void* 
     return LYS_OK;
 }
 
-static int csr_n_warps() { return sm_count() * CSR_WARPS; }
+static int csr_warps_per_cta(int K) { return std::max(1, std::min(CSR_WARPS, (int)((200 * 1024) / ((size_t)K * 4)))); }
+static int csr_n_warps(int K) { return sm_count() * csr_warps_per_cta(K); }
 
 extern "C" size_t lys_atom_csr_workspace_bytes(int K, int64_t N, int k)
 {
     (void)N; (void)k;
-    return align_up((size_t)csr_n_warps() * (size_t)K * 4, 256);
+    return align_up((size_t)csr_n_warps(K) * (size_t)K * 4, 256);
 }
 
 extern "C" int lys_build_atom_csr(const int32_t* idx, const float* val, int64_t N, int k, int K,
@@ -355,20 +374,20 @@ extern "C" int lys_build_atom_csr(const int32_t* idx, const float* val, int64_t 
     LYS_CHECK_ARG(N * (int64_t)k < (1ll << 31), "lys_build_atom_csr: N*k must fit int32");
     if (workspace_bytes < lys_atom_csr_workspace_bytes(K, N, k)) { set_error("lys_build_atom_csr: workspace too small"); return LYS_EWORKSPACE; }
     int32_t* hist = reinterpret_cast<int32_t*>(workspace);
-    const int nw = csr_n_warps();
+    const int nw = csr_n_warps(K), wpc = csr_warps_per_cta(K);
     const int64_t E = N * (int64_t)k;
     int64_t per_warp = (E + nw - 1) / nw;
     per_warp = std::max<int64_t>(32, (per_warp + 31) / 32 * 32);
-    size_t smem = sizeof(int32_t) * (size_t)CSR_WARPS * K;
+    size_t smem = sizeof(int32_t) * (size_t)wpc * K;
     if (smem > 48 * 1024) {
         LYS_CUDA(cudaFuncSetAttribute(csr_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LYS_CUDA(cudaFuncSetAttribute(csr_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    csr_hist_kernel<<<nw / CSR_WARPS, CSR_WARPS * 32, smem, stream>>>(idx, val, E, K, per_warp, hist);
+    csr_hist_kernel<<<nw / wpc, wpc * 32, smem, stream>>>(idx, val, E, K, per_warp, hist);
     LYS_LAUNCH_CHECK("csr_hist_kernel");
     csr_scan_kernel<<<1, 1024, 0, stream>>>(hist, nw, K, rowptr);
     LYS_LAUNCH_CHECK("csr_scan_kernel");
-    csr_fill_kernel<<<nw / CSR_WARPS, CSR_WARPS * 32, smem, stream>>>(idx, val, E, K, per_warp, hist, rowptr, entries);
+    csr_fill_kernel<<<nw / wpc, wpc * 32, smem, stream>>>(idx, val, E, K, per_warp, hist, rowptr, entries);
     LYS_LAUNCH_CHECK("csr_fill_kernel");
     return LYS_OK;
 }
