@@ -99,6 +99,28 @@ LYS_API int lys_corr_gemm(const float* X, int64_t x_feat_stride, int64_t x_sig_s
                           const float* D, int64_t ldd, int n, int K, int64_t C, float* alpha,
                           int impl, void* stream);
 
+/* ---- sibling coders on the same correlation front end -----------------------------------
+ * lys_thresh_encode replaces algorithm 'thresh' (lyssa/sparse_coding.py:636-641 dispatch,
+ * :416-425 thresholding): Alpha = D^T X, every signal keeps its k LARGEST SIGNED correlations,
+ * Z = Alpha there.  k in [1, K] (nonzero_percentage is resolved by the host: floor(p*K), :420).
+ * lys_iht_encode replaces algorithm 'iht' (:671-690, :433-446): Z0 = thresh, then n_iter times
+ * Z <- Z - eta * D^T (D Z - X) followed by keeping the k largest |Z| per signal; k <= 32.
+ * Outputs and Z addressing as lys_bomp_encode; codes come out in descending order of the
+ * selection key, ties to the lower atom index (the reference's argsort order on exact ties is
+ * unspecified).  No Gram matrix is needed. */
+LYS_API size_t lys_thresh_workspace_bytes(int n, int K, int64_t N);
+LYS_API int lys_thresh_encode(const float* X, int64_t x_feat_stride, int64_t x_sig_stride,
+                      const float* D, int64_t ldd, int n, int K, int64_t N, int k,
+                      int32_t* idx, float* val, int32_t* nsel,
+                      float* Z, int64_t z_atom_stride, int64_t z_sig_stride,
+                      void* workspace, size_t workspace_bytes, void* stream);
+LYS_API size_t lys_iht_workspace_bytes(int n, int K, int64_t N);
+LYS_API int lys_iht_encode(const float* X, int64_t x_feat_stride, int64_t x_sig_stride,
+                   const float* D, int64_t ldd, int n, int K, int64_t N, int k, float eta, int n_iter,
+                   int32_t* idx, float* val, int32_t* nsel,
+                   float* Z, int64_t z_atom_stride, int64_t z_sig_stride,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
 /* Same call for HOST buffers (what `sparse_encoder.encode(X, D)` is for NumPy arrays):
  * uploads D, forms the Gram matrix, streams X through the device in chunks with copies
  * overlapped with compute, writes idx/val/nsel and/or dense Z back to host memory.

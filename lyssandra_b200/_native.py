@@ -26,6 +26,12 @@ SIGNATURES = {
     "lys_bomp_workspace_bytes": (c_sz, [c_int, c_int, c_i64, c_int]),
     "lys_bomp_encode": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_i64, c_int,
                                 c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_sz, c_vp]),
+    "lys_thresh_workspace_bytes": (c_sz, [c_int, c_int, c_i64]),
+    "lys_thresh_encode": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_i64, c_int,
+                                  c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_sz, c_vp]),
+    "lys_iht_workspace_bytes": (c_sz, [c_int, c_int, c_i64]),
+    "lys_iht_encode": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_i64, c_int, ctypes.c_float, c_int,
+                               c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_sz, c_vp]),
     "lys_corr_gemm": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_i64, c_vp, c_int, c_vp]),
     "lys_bomp_encode_host": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_i64, c_int,
                                      c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int]),

@@ -95,9 +95,9 @@ __global__ void dense_fill_kernel(const int32_t* __restrict__ idx, const float* 
             for (int c = lane; c < K; c += 32) z[(int64_t)c * zas] = 0.f;
         }
         __syncwarp();
-        if (lane < k) {
-            int a = idx[i * k + lane];
-            if (a >= 0) z[(int64_t)a * zas] = val[i * k + lane];
+        for (int j = lane; j < k; j += 32) {
+            int a = idx[i * k + j];
+            if (a >= 0) z[(int64_t)a * zas] = val[i * k + j];
         }
     }
 }
@@ -234,7 +234,7 @@ extern "C" int lys_codes_to_dense(const int32_t* idx, const float* val, int64_t 
                                   float* Z, int64_t zas, int64_t zss, void* stream)
 {
     LYS_CHECK_ARG(idx && val && Z, "lys_codes_to_dense: null pointer");
-    LYS_CHECK_ARG(k >= 1 && k <= LYS_MAX_NONZERO && K >= 1 && N >= 0, "lys_codes_to_dense: bad shape");
+    LYS_CHECK_ARG(k >= 1 && k <= K && K >= 1 && N >= 0, "lys_codes_to_dense: bad shape");
     if (N == 0) return LYS_OK;
     int64_t blocks = std::min<int64_t>((N + 7) / 8, (int64_t)sm_count() * 8);
     dense_fill_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(idx, val, N, k, K, Z, zas, zss);

@@ -134,6 +134,49 @@ def bomp_encode(X, D, k, G=None, dense=False):
     return codes
 
 
+def _threshold_encode(kind, X, D, k, eta, n_iter, dense):
+    lib = nat.load()
+    n, N = X.shape
+    n2, K = D.shape
+    if n != n2:
+        raise ValueError("X has %d features but D has %d" % (n, n2))
+    if k is None:
+        raise ValueError("params['n_nonzero_coefs'] (or 'nonzero_percentage') must be set for algorithm %r" % kind)
+    k = int(k)
+    dev = X.device
+    with torch.cuda.device(dev):
+        idx = torch.empty((N, k), dtype=torch.int32, device=dev)
+        val = torch.empty((N, k), dtype=torch.float32, device=dev)
+        nsel = torch.empty((N,), dtype=torch.int32, device=dev)
+        Zt = torch.empty((N, K), dtype=torch.float32, device=dev) if dense else None
+        if kind == "thresh":
+            ws = workspace(dev, lib.lys_thresh_workspace_bytes(n, K, N))
+            nat.check(lib.lys_thresh_encode(
+                _ptr(X), X.stride(0), X.stride(1), _ptr(D), D.stride(0), n, K, N, k,
+                _ptr(idx), _ptr(val), _ptr(nsel), _ptr(Zt), 1, K, _ptr(ws), ws.numel(), _stream_ptr(dev)))
+        else:
+            ws = workspace(dev, lib.lys_iht_workspace_bytes(n, K, N))
+            nat.check(lib.lys_iht_encode(
+                _ptr(X), X.stride(0), X.stride(1), _ptr(D), D.stride(0), n, K, N, k, float(eta), int(n_iter),
+                _ptr(idx), _ptr(val), _ptr(nsel), _ptr(Zt), 1, K, _ptr(ws), ws.numel(), _stream_ptr(dev)))
+    codes = SparseCodes(idx, val, nsel, K)
+    if dense:
+        return codes, Zt.t()
+    return codes
+
+
+def thresh_encode(X, D, k, dense=False):
+    """Alpha = D^T X, keep the k largest signed correlations per signal
+    (lyssa/sparse_coding.py:636-641,:416-425).  Device tensors; returns like bomp_encode."""
+    return _threshold_encode("thresh", X, D, k, 0.0, 0, dense)
+
+
+def iht_encode(X, D, k, eta, n_iter, dense=False):
+    """Iterative hard thresholding started from thresh_encode (lyssa/sparse_coding.py:671-690,
+    :433-446)."""
+    return _threshold_encode("iht", X, D, k, eta, n_iter, dense)
+
+
 def bomp_encode_host(X, D, k, dense=True, device=None, want_codes=True):
     """Same for HOST arrays (numpy float32): chunked, copy/compute-overlapped pipeline inside the
     library.  Returns (idx, val, nsel, Z) as numpy arrays (Z a transposed view, or None)."""

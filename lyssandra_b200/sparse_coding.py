@@ -1,11 +1,12 @@
 """Mirror of ``lyssa.sparse_coding.sparse_encoder`` for the Batch-OMP hot path
 (/root/reference/lyssa/sparse_coding.py:587-603 constructor + encode/__call__,
-:629-635 the 'bomp' branch, :706 the unknown-algorithm error, :708-726 dispatch).
+:629-635 the 'bomp' branch, :706 the unknown-algorithm error, :708-726 dispatch) and the two
+thresholding coders that share its correlation front end (:636-641 'thresh', :671-690 'iht').
 
-Only ``algorithm='bomp'`` runs — on the GPU, through liblyssa_b200.so.  The reference's other
-coders are outside this engine's scope and raise NotImplementedError rather
-than silently running on the CPU; an unknown name raises ValueError exactly like the
-reference.  The public attributes (algorithm, params, n_jobs, verbose, mmap, name) are plain
+``algorithm`` 'bomp', 'thresh' and 'iht' run — on the GPU, through liblyssa_b200.so.  The
+reference's other coders are outside this engine's scope and raise
+NotImplementedError rather than silently running on the CPU; an unknown name raises ValueError
+exactly like the reference.  The public attributes (algorithm, params, n_jobs, verbose, mmap, name) are plain
 and mutable because reference callers mutate them (ksvd.py:159, online_dict_learn.py:41).
 """
 from __future__ import annotations
@@ -54,42 +55,70 @@ class sparse_encoder(object):
         return self.__call__(X, D)
 
     def __call__(self, X, D):
-        k = self._check()
+        k = self._check(D.shape[1])
         if torch.is_tensor(X) and X.is_cuda:
             Dd = engine.as_dictionary(D, X.device)
             Xd = engine.as_device_matrix(X, X.device)
-            _, Z = engine.bomp_encode(Xd, Dd, k, dense=True)
-            return Z
+            return self._encode_device(Xd, Dd, k, dense=True)[1]
         Xh, Dh = self._host_arrays(X, D)
+        if self.algorithm != "bomp":
+            Xd = engine.as_device_matrix(Xh, None)
+            Dd = engine.as_dictionary(Dh, Xd.device)
+            return self._encode_device(Xd, Dd, k, dense=True)[1].cpu().numpy()
         return self._encode_host(Xh, Dh, k, dense=True)[3]
+
+    def _encode_device(self, Xd, Dd, k, dense, G=None):
+        if self.algorithm == "thresh":
+            out = engine.thresh_encode(Xd, Dd, k, dense=dense)
+        elif self.algorithm == "iht":
+            out = engine.iht_encode(Xd, Dd, k, self.params.get("eta"), self.params.get("n_iter"), dense=dense)
+        else:
+            out = engine.bomp_encode(Xd, Dd, k, G=G, dense=dense)
+        return out if dense else (out, None)
 
     # ------------------------------------------------------------------------ extensions
     def encode_sparse(self, X, D, G=None):
         """Device-resident sparse codes; X/D may be NumPy (uploaded) or CUDA tensors."""
-        k = self._check()
+        k = self._check(D.shape[1])
         Xd = engine.as_device_matrix(X, X.device if torch.is_tensor(X) and X.is_cuda else None)
         Dd = engine.as_dictionary(D, Xd.device)
-        return engine.bomp_encode(Xd, Dd, k, G=G, dense=False)
+        return self._encode_device(Xd, Dd, k, dense=False, G=G)[0]
 
     def encode_sparse_host(self, X, D):
         """NumPy in, NumPy (idx, val, nsel) out — no dense Z crosses PCIe."""
-        k = self._check()
+        k = self._check(np.shape(D)[1])
         Xh, Dh = self._host_arrays(X, D)
+        if self.algorithm != "bomp":
+            codes = self.encode_sparse(Xh, Dh)
+            return codes.idx.cpu().numpy(), codes.val.cpu().numpy(), codes.nsel.cpu().numpy()
         idx, val, nsel, _ = self._encode_host(Xh, Dh, k, dense=False)
         return idx, val, nsel
 
     # --------------------------------------------------------------------------- helpers
-    def _check(self):
-        if self.algorithm != "bomp":
-            if self.algorithm in _REFERENCE_ALGORITHMS:
+    def _check(self, n_atoms=None):
+        alg = self.algorithm
+        if alg not in ("bomp", "thresh", "iht"):
+            if alg in _REFERENCE_ALGORITHMS:
                 raise NotImplementedError(
-                    "algorithm %r is outside the B200 engine's scope: only 'bomp' is implemented "
-                    "(no CPU fallback by design)" % (self.algorithm,))
+                    "algorithm %r is outside the B200 engine's scope: 'bomp', 'thresh' and 'iht' are "
+                    "implemented (no CPU fallback by design)" % (alg,))
             raise ValueError("Sparse optimizer not found.")          # sparse_coding.py:706
         k = self.params.get("n_nonzero_coefs")
+        pct = self.params.get("nonzero_percentage")
+        if alg != "bomp" and pct is not None:
+            if n_atoms is None:
+                raise ValueError("nonzero_percentage needs the dictionary size")
+            kp = int(np.floor(pct * n_atoms))                        # sparse_coding.py:419-420
+            if alg == "iht" and k is not None and int(k) != kp:
+                # the reference thresholds the start with floor(p*K) and the iterations with
+                # n_nonzero_coefs (:676-690); the engine runs one sparsity throughout
+                raise ValueError("'iht': nonzero_percentage and n_nonzero_coefs disagree (%d vs %d)" % (kp, int(k)))
+            k = kp
         if k is None:
             # the reference crashes inside np.zeros((None, None)) (sparse_coding.py:317, quirk Q2)
-            raise ValueError("params['n_nonzero_coefs'] must be set for algorithm 'bomp'")
+            raise ValueError("params['n_nonzero_coefs'] must be set for algorithm %r" % (alg,))
+        if alg == "iht" and (self.params.get("eta") is None or self.params.get("n_iter") is None):
+            raise ValueError("params['eta'] and params['n_iter'] must be set for algorithm 'iht'")
         return int(k)
 
     @staticmethod

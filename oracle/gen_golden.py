@@ -10,6 +10,7 @@ are the known-answer tests SURVEY.md §8c asks the new repo to author.
 from __future__ import annotations
 
 import os
+import sys
 
 import numpy as np
 
@@ -36,9 +37,31 @@ def _bomp(ref, X, D, k):
         return ref.sparse_encoder(algorithm="bomp", params={"n_nonzero_coefs": k}, verbose=False).encode(X, D)
 
 
+def thresh_section(ref):
+    """the 'thresh' and 'iht' coders of the live reference on seeded patches
+    (n=64; K=256 exercises the fp32 GEMM front end, K=100 the generic shapes)."""
+    out = {}
+    for tag, K, N in (("a", 256, 200), ("b", 100, 120)):
+        X = lo.synthetic_patches(N, 64, seed=40 + K)
+        D = lo.synthetic_dictionary(K, 64, seed=41 + K)
+        out["X_" + tag], out["D_" + tag] = np.ascontiguousarray(X), D
+        cases = (("thresh_k5", "thresh", {"n_nonzero_coefs": 5}, 5),
+                 ("thresh_p10", "thresh", {"nonzero_percentage": 0.1}, int(np.floor(0.1 * K))),
+                 ("iht_k5", "iht", {"n_nonzero_coefs": 5, "eta": 0.2, "n_iter": 4}, 5),
+                 ("iht_k3_it0", "iht", {"n_nonzero_coefs": 3, "eta": 0.2, "n_iter": 0}, 3))
+        for name, alg, params, k in cases:
+            with rl.quiet():
+                Z = ref.sparse_encoder(algorithm=alg, params=dict(params), verbose=False).encode(X.astype(float), D.astype(float))
+            out["idx_%s_%s" % (name, tag)], out["val_%s_%s" % (name, tag)] = _sparse(Z, k)
+    np.savez_compressed(os.path.join(OUT, "thresh.npz"), **out)
+
+
 def main():
     ref = rl.load()
     os.makedirs(OUT, exist_ok=True)
+    if sys.argv[1:] == ["thresh"]:
+        thresh_section(ref)
+        return
 
     # ---- (7) seeded random, BASELINE cfg1 shape cut to 512 signals: n=64, K=256, k=5
     X = lo.synthetic_patches(512, 64, seed=0)
@@ -184,6 +207,8 @@ def main():
         out["feat_%d_%d" % (gs, ps)] = f
         out["pos_%d_%d" % (gs, ps)] = p
     np.savez_compressed(os.path.join(OUT, "dsift.npz"), **out)
+
+    thresh_section(ref)
 
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

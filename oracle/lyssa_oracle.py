@@ -148,13 +148,39 @@ def _single_thread_blas():
         pass
 
 
+def thresholding(Alpha, nonzero_percentage=None, n_nonzero_coefs=None):
+    """Keep the n_nonzero_coefs largest SIGNED correlations of every signal —
+    lyssa/sparse_coding.py:416-425 (argsort ascending, reversed, first k)."""
+    n_atoms, n_samples = Alpha.shape
+    Z = np.zeros((n_atoms, n_samples))
+    if nonzero_percentage is not None:
+        n_nonzero_coefs = int(np.floor(nonzero_percentage * n_atoms))      # :419-420
+    for i in range(n_samples):
+        keep = Alpha[:, i].argsort()[::-1][:n_nonzero_coefs]                # :423
+        Z[keep, i] = Alpha[keep, i]
+    return Z
+
+
+def iterative_hard_thresh(X, Z0, R0, D, eta=None, n_nonzero_coefs=None, n_iter=None):
+    """Z <- Z - eta D^T R; zero all but the k largest |Z| per signal; R = D Z - X —
+    lyssa/sparse_coding.py:433-446."""
+    Z, R = Z0, R0
+    for _ in range(n_iter):
+        Z -= eta * np.dot(D.T, R)                                           # :439
+        for i in range(X.shape[1]):
+            drop = np.abs(Z[:, i]).argsort()[::-1][n_nonzero_coefs:]        # :442
+            Z[drop, i] = 0
+        R = np.dot(D, Z) - X                                                # :444
+    return Z
+
+
 class sparse_encoder(object):
     """The 'bomp' branch of lyssa.sparse_coding.sparse_encoder — sparse_coding.py:587-603,
-    :629-635 (Gram, Alpha, partial(batch_omp)), :708-726 (run_parallel with n_batches=100).
-    Unknown algorithms raise ValueError (:706).  Only what the hot path needs is restated:
-    'bomp' (and nothing else); n_jobs>1 reproduces run_parallel's regime — a process pool
-    over 100 contiguous column batches with one BLAS thread per worker
-    (lyssa/utils/__init__.py:92-146, sparse_coding.py:713-716)."""
+    :629-635 (Gram, Alpha, partial(batch_omp)), :708-726 (run_parallel with n_batches=100) —
+    plus the two thresholding coders on the same correlations: 'thresh' (:636-641) and 'iht'
+    (:671-690).  Unknown algorithms raise ValueError (:706).  n_jobs>1 ('bomp') reproduces
+    run_parallel's regime — a process pool over 100 contiguous column batches with one BLAS
+    thread per worker (lyssa/utils/__init__.py:92-146, sparse_coding.py:713-716)."""
 
     def __init__(self, algorithm="omp", params=None, n_jobs=1, verbose=True, mmap=False, name="sparse_coder"):
         self.name = name
@@ -170,10 +196,20 @@ class sparse_encoder(object):
         return self.__call__(X, D)
 
     def __call__(self, X, D):
+        if self.algorithm in ("thresh", "iht"):
+            alpha = np.dot(D.T, X)                                   # :637 / :672
+            Z = thresholding(alpha, n_nonzero_coefs=self.params.get("n_nonzero_coefs"),
+                             nonzero_percentage=self.params.get("nonzero_percentage"))
+            if self.algorithm == "iht":
+                R0 = np.dot(D, Z) - X                                # :682
+                Z = iterative_hard_thresh(X, Z, R0, D, eta=self.params.get("eta"),
+                                          n_nonzero_coefs=self.params.get("n_nonzero_coefs"),
+                                          n_iter=self.params.get("n_iter"))
+            return Z
         if self.algorithm != "bomp":
-            if self.algorithm in ("omp", "thresh", "nnomp", "group_omp", "sparse_group_omp",
-                                  "somp", "iht", "lasso", "llc"):
-                raise NotImplementedError("oracle restates only the 'bomp' hot path")
+            if self.algorithm in ("omp", "nnomp", "group_omp", "sparse_group_omp",
+                                  "somp", "lasso", "llc"):
+                raise NotImplementedError("oracle restates only 'bomp', 'thresh' and 'iht'")
             raise ValueError("Sparse optimizer not found.")
         k = self.params.get("n_nonzero_coefs")
         n_atoms, n_signals = D.shape[1], X.shape[1]

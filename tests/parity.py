@@ -49,3 +49,43 @@ def check_codes(idx_gpu, val_gpu, idx_ref, val_ref, ok=None, coef_tol=COEF_TOL, 
     assert err <= coef_tol, "%s: coefficient rel-inf error %.3g > %.3g" % (label, err, coef_tol)
     return {"columns": int(N), "compared": int(both.sum()), "excluded": int((~ok).sum()),
             "mismatch_in_excluded": int((~ok & ~same).sum()), "coef_rel_inf": float(err)}
+
+
+def thresh_trace(X, D, k, eta=None, n_iter=0):
+    """float64 replay of the oracle's 'thresh' (n_iter == 0) / 'iht' coders that also returns, per
+    column, the smallest relative gap between the k-th and (k+1)-th selection keys met at any stage
+    (signed alpha for the start, |Z| for the iterations).  Columns whose gap is below GAP_TOL are
+    near-ties: float32 rounding alone can swap the two entries."""
+    X = np.asarray(X, dtype=np.float64); D = np.asarray(D, dtype=np.float64)
+    K, N = D.shape[1], X.shape[1]
+    A = D.T @ X
+    gap = np.full(N, np.inf)
+
+    def keep_top(keys, vals):
+        order = np.argsort(-keys, axis=0, kind="stable")
+        top = order[:k]
+        Z = np.zeros_like(vals)
+        np.put_along_axis(Z, top, np.take_along_axis(vals, top, axis=0), axis=0)
+        if k < K:
+            ks = np.take_along_axis(keys, order[k - 1:k + 1], axis=0)
+            g = (ks[0] - ks[1]) / np.maximum(np.max(np.abs(keys), axis=0), 1e-300)
+            np.minimum(gap, g, out=gap)
+        return Z
+
+    Z = keep_top(A, A)
+    for _ in range(int(n_iter)):
+        V = Z - eta * (D.T @ (D @ Z - X))
+        Z = keep_top(np.abs(V), V)
+    return Z, gap
+
+
+def dense_to_codes(Z, k):
+    """dense (K,N) -> (idx, val)[N,k], ascending atom index, -1 padded."""
+    K, N = Z.shape
+    idx = -np.ones((N, k), dtype=np.int64)
+    val = np.zeros((N, k))
+    for i in range(N):
+        nz = np.flatnonzero(Z[:, i])
+        idx[i, :len(nz)] = nz
+        val[i, :len(nz)] = Z[nz, i]
+    return idx, val

@@ -33,6 +33,20 @@ def test_other_reference_coders_do_not_fall_back_to_cpu():
         sparse_encoder(algorithm="bomp", params={}).encode(np.zeros((4, 3)), np.eye(4))
 
 
+def test_thresholding_coder_parameters():
+    # nonzero_percentage -> floor(p * n_atoms) (sparse_coding.py:419-420), and it wins over n_nonzero_coefs
+    assert sparse_encoder("thresh", {"nonzero_percentage": 0.1})._check(256) == 25
+    assert sparse_encoder("thresh", {"nonzero_percentage": 0.1, "n_nonzero_coefs": 3})._check(100) == 10
+    assert sparse_encoder("thresh", {"n_nonzero_coefs": 3})._check(100) == 3
+    with pytest.raises(ValueError):
+        sparse_encoder("thresh", {})._check(100)
+    with pytest.raises(ValueError, match="eta"):
+        sparse_encoder("iht", {"n_nonzero_coefs": 3})._check(100)
+    with pytest.raises(ValueError, match="disagree"):
+        sparse_encoder("iht", {"n_nonzero_coefs": 3, "nonzero_percentage": 0.1, "eta": 0.1, "n_iter": 2})._check(100)
+    assert sparse_encoder("iht", {"n_nonzero_coefs": 3, "eta": 0.1, "n_iter": 2})._check(100) == 3
+
+
 def test_public_attributes_are_mutable_like_the_reference():
     se = sparse_encoder(algorithm="bomp", params={"n_nonzero_coefs": 3}, n_jobs=2, verbose=True)
     se.mmap = True; se.verbose = False; se.params["n_nonzero_coefs"] = 5; se.n_jobs = 1

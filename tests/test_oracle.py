@@ -201,3 +201,37 @@ def test_dsift_oracle_matches_live_reference():
     fr, pr = ref.DsiftExtractor(grid_spacing=5, patch_size=12).process_image(img)
     fo, po = lo.DsiftExtractor(grid_spacing=5, patch_size=12).process_image(img)
     assert np.array_equal(fr, fo) and np.array_equal(pr, po)
+
+
+_THRESH_CASES = (("thresh_k5", "thresh", {"n_nonzero_coefs": 5}, 5),
+                 ("thresh_p10", "thresh", {"nonzero_percentage": 0.1}, None),
+                 ("iht_k5", "iht", {"n_nonzero_coefs": 5, "eta": 0.2, "n_iter": 4}, 5),
+                 ("iht_k3_it0", "iht", {"n_nonzero_coefs": 3, "eta": 0.2, "n_iter": 0}, 3))
+
+
+def test_thresh_iht_oracle_matches_golden(golden):
+    """restated 'thresh' / 'iht' coders reproduce the live reference's codes
+    (tests/golden/thresh.npz, made by `python -m oracle.gen_golden thresh`)."""
+    from parity import dense_to_codes
+    g = golden("thresh")
+    for tag in ("a", "b"):
+        X, D = g["X_" + tag].astype(np.float64), g["D_" + tag].astype(np.float64)
+        for name, alg, params, k in _THRESH_CASES:
+            k = int(np.floor(0.1 * D.shape[1])) if k is None else k
+            Z = lo.sparse_encoder(alg, dict(params), verbose=False).encode(X, D)
+            idx, val = dense_to_codes(Z, k)
+            assert np.array_equal(idx, g["idx_%s_%s" % (name, tag)]), (name, tag)
+            assert np.max(np.abs(val - g["val_%s_%s" % (name, tag)])) < 1e-12, (name, tag)
+
+
+@pytest.mark.skipif(not rl.available(), reason="reference tree not present (GPU box)")
+def test_thresh_iht_oracle_matches_live_reference():
+    ref = rl.load()
+    X = lo.synthetic_patches(150, 64, seed=71).astype(np.float64)
+    D = lo.synthetic_dictionary(90, 64, seed=72).astype(np.float64)
+    for alg, params in (("thresh", {"n_nonzero_coefs": 7}), ("thresh", {"nonzero_percentage": 0.25}),
+                        ("iht", {"n_nonzero_coefs": 6, "eta": 0.1, "n_iter": 3})):
+        with rl.quiet():
+            Zr = ref.sparse_encoder(algorithm=alg, params=dict(params), verbose=False).encode(X, D)
+        Zo = lo.sparse_encoder(alg, dict(params), verbose=False).encode(X, D)
+        assert np.array_equal(Zr, Zo), alg
