@@ -197,6 +197,35 @@ __device__ __forceinline__ void store_planes(unsigned char* slotA, int row, cons
     }
 }
 
+// 'thresh' mode (lyssa/sparse_coding.py:416-425): running top-KNZ of the SIGNED correlations of one signal,
+// descending, ties to the lower column (columns arrive in ascending order and only a strictly larger value
+// displaces an entry).
+template <int KNZ> struct TopK {
+    float t[KNZ];
+    int c[KNZ];
+};
+template <int KNZ> __device__ __forceinline__ void topk_insert(TopK<KNZ>& tk, float v, int col)
+{
+    tk.t[KNZ - 1] = v;
+    tk.c[KNZ - 1] = col;
+#pragma unroll
+    for (int m = KNZ - 1; m > 0; --m) {
+        const bool sw = tk.t[m] > tk.t[m - 1];
+        const float a = tk.t[m - 1], b = tk.t[m];
+        const int ca = tk.c[m - 1], cb = tk.c[m];
+        tk.t[m - 1] = sw ? b : a; tk.t[m] = sw ? a : b;
+        tk.c[m - 1] = sw ? cb : ca; tk.c[m] = sw ? ca : cb;
+    }
+}
+template <int KNZ> __device__ __forceinline__ void scan_piece_topk(const uint32_t (&r)[32], int piece, TopK<KNZ>& tk)
+{
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const float v = __uint_as_float(r[i]);
+        if (v > tk.t[KNZ - 1]) topk_insert(tk, v, piece * 32 + i);
+    }
+}
+
 template <int KNZ> struct SigState {
     float r[NF];                // residual r_j (r_0 = x)
     float L[KNZ][KNZ];          // L[j][m], m < j: Cholesky row of step j (unit diagonal of G assumed, quirk Q1)
@@ -304,7 +333,9 @@ constexpr int NS = 2;                    // tiles ("slots") interleaved per CTA
 constexpr int THREADS = (NS + 1) * 128;
 constexpr int ZB = 16384;                // block of zeros, source of the bulk stores that zero-fill dense rows
 
-template <int KNZ, int PAIR, bool TIMING>
+// MODE 0: Batch-OMP (k greedy steps per tile).  MODE 1: 'thresh' — one correlation pass per tile, the scan keeps
+// the k largest signed correlations, coefficients are the exact fp32 dot products with the picked atoms.
+template <int KNZ, int PAIR, bool TIMING, int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                const uint4* __restrict__ planes, const float* __restrict__ Dt, const float* __restrict__ G,
@@ -328,6 +359,7 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
     const uint32_t rank = (PAIR == 2) ? cluster_ctarank() : 0u;
     const int unit = (PAIR == 2) ? (int)cluster_id_x() : (int)blockIdx.x;
     const int64_t n_tiles = (N + TM - 1) / TM;
+    const int steps = (MODE == 0) ? k : 1;             // correlation passes per tile
 
     if (tid == 0) {
         tile_ready[0] = 0u; tile_ready[1] = 0u;
@@ -370,8 +402,8 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                 PhaseTimer<TIMING> pt;
                 pt.start();
                 for (int r = 0; r < rounds; ++r) {
-                    for (int j = 0; j < k; ++j) {
-                        const uint32_t q = (uint32_t)(r * k + j);
+                    for (int j = 0; j < steps; ++j) {
+                        const uint32_t q = (uint32_t)(r * steps + j);
 #pragma unroll 1
                         for (int s = 0; s < NS; ++s) {
                             mbar_wait(bar_local + 8 * s, q & 1);                  // planes of r_j landed (both CTAs)
@@ -517,6 +549,58 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
             st.cnt = 0;
             st.done = !live;
             pt.lap(0, lane);
+            if constexpr (MODE == 1) {
+                TopK<KNZ> tk;
+#pragma unroll
+                for (int m = 0; m < KNZ; ++m) { tk.t[m] = -INFINITY; tk.c[m] = -1; }
+                const uint32_t qq = (uint32_t)r;
+                const uint32_t u0 = (qq * NS + s) * (uint32_t)nch;
+#pragma unroll 1
+                for (int c = 0; c < nch; ++c) {
+                    const uint32_t stg = (u0 + c) & (NSTG - 1);
+                    mbar_wait(bar_local + 8 * (8 + 8 * s + c), qq & 1);
+                    fence_after();
+                    const uint32_t ta = tq + stg * CH;
+                    uint32_t b0[32], b1[32];
+                    LYS_TMEM_LD_X32(ta, b0);
+#pragma unroll 1
+                    for (int sc = 0; sc < NP; sc += 2) {
+                        LYS_TMEM_WAIT_X32(b0);
+                        LYS_TMEM_LD_X32(ta + (sc + 1) * 32, b1);
+                        scan_piece_topk<KNZ>(b0, c * NP + sc, tk);
+                        LYS_TMEM_WAIT_X32(b1);
+                        if (sc + 2 < NP) LYS_TMEM_LD_X32(ta + (sc + 2) * 32, b0);
+                        else {
+                            fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * (24 + 8 * s + c));
+                        }
+                        scan_piece_topk<KNZ>(b1, c * NP + sc + 1, tk);
+                    }
+                }
+                if (live) {
+                    // Z = Alpha on the kept entries (:424): the exact fp32 correlation, not the tensor-core ranking value
+#pragma unroll
+                    for (int m = 0; m < KNZ; ++m) {
+                        if (m < k) {
+                            const int col = tk.c[m];
+                            float acc = 0.f;
+                            if (col >= 0) {
+                                const float4* dp = reinterpret_cast<const float4*>(Dt + (size_t)col * NF);
+#pragma unroll
+                                for (int q4 = 0; q4 < NF / 4; ++q4) {
+                                    const float4 d4 = __ldg(dp + q4);
+                                    acc = fmaf(d4.x, st.r[4 * q4], acc); acc = fmaf(d4.y, st.r[4 * q4 + 1], acc);
+                                    acc = fmaf(d4.z, st.r[4 * q4 + 2], acc); acc = fmaf(d4.w, st.r[4 * q4 + 3], acc);
+                                }
+                            }
+                            idx[sig * k + m] = col;
+                            val[sig * k + m] = acc;
+                        }
+                    }
+                    if (nsel) nsel[sig] = k;
+                }
+            } else {
             for (int j = 0; j < k; ++j) {
                 // ---- :322 argmax |alpha_j| over all atoms, first maximum
                 ArgmaxStateR am;
@@ -593,6 +677,7 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                 }
                 if (nsel) nsel[sig] = st.cnt;
             }
+            }   // MODE 0
             if (Z && tile < n_tiles) {                 // hand the tile to the dense-row writer of this slot
                 __syncwarp();
                 if (lane == 0) { __threadfence(); atomicAdd(tile_ready + s, 1u); }
@@ -654,7 +739,7 @@ size_t dt_bytes(int K) { return (size_t)K * NF * sizeof(float); }
 // orthonormalised directions u_0..u_{k-3} of every signal in flight: [CTA][slot][vector][feature][signal]
 size_t scratch_bytes(int k) { return (size_t)sm_count() * MAX_SLOTS * (k > 2 ? k - 2 : 0) * NF * TM * sizeof(float); }
 
-template <int KNZ, int PAIR>
+template <int KNZ, int PAIR, int MODE = 0>
 int launch_tc(const float* X, int64_t xfs, int64_t xss, int n, const void* planes, const float* Dt, const float* G,
               int K, int64_t N, int k, int32_t* idx, float* val, int32_t* nsel, float* Z, int64_t zss,
               float* scratch, cudaStream_t stream)
@@ -663,7 +748,7 @@ int launch_tc(const float* X, int64_t xfs, int64_t xss, int n, const void* plane
     const int nch = K / CH;
     const size_t smem = (size_t)nch * GE::B_CHUNK + (size_t)NS * A_SLOT + SMEM_BAR + NS * ZB;
     static const bool timing = getenv("LYS_TC_TIMING") != nullptr;
-    auto kern = timing ? bomp_tc_kernel<KNZ, PAIR, true> : bomp_tc_kernel<KNZ, PAIR, false>;
+    auto kern = (timing && MODE == 0) ? bomp_tc_kernel<KNZ, PAIR, (MODE == 0), MODE> : bomp_tc_kernel<KNZ, PAIR, false, MODE>;
     LYS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n_tiles = (N + TM - 1) / TM;
     const int64_t tiles_per_unit = (int64_t)PAIR * NS;
@@ -737,6 +822,35 @@ int bomp_encode_fused(const float* X, int64_t xfs, int64_t xss, const float* D, 
     }
     if (prof) cudaEventRecord(stop_ev, stream);
     return rc;
+}
+
+size_t thresh_fused_workspace_bytes(int n, int K, int64_t, int k)
+{
+    if (!fused_shape_ok(n, K, k)) return 0;
+    return align_up(planes_bytes(K), 256) + align_up(dt_bytes(K), 256) + 256;
+}
+
+// 'thresh' coder through the fused kernel (MODE 1): same shapes and Z layout rules as bomp_encode_fused
+int thresh_encode_fused(const float* X, int64_t xfs, int64_t xss, const float* D, int64_t ldd,
+                        int n, int K, int64_t N, int k, int32_t* idx, float* val, int32_t* nsel,
+                        float* Z, int64_t zas, int64_t zss, void* workspace, size_t workspace_bytes, cudaStream_t stream)
+{
+    if (!fused_shape_ok(n, K, k) || getenv("LYS_THRESH_PATH")) return LYS_EUNSUPPORTED;
+    if (Z && (zas != 1 || (zss % 4) != 0 || (reinterpret_cast<uintptr_t>(Z) & 15) != 0)) return LYS_EUNSUPPORTED;
+    if (workspace_bytes < thresh_fused_workspace_bytes(n, K, N, k)) return LYS_EWORKSPACE;
+    unsigned char* planes = reinterpret_cast<unsigned char*>(workspace);
+    float* Dt = reinterpret_cast<float*>(planes + align_up(planes_bytes(K), 256));
+    const int pair = (K > 512) ? 2 : 1;
+    const int nch = K / CH;
+    const int items = K * (NF / 8);
+    if (pair == 2) prep_dict_kernel<2><<<(items + 255) / 256, 256, 0, stream>>>(D, ldd, n, K, nch, planes, Dt);
+    else prep_dict_kernel<1><<<(items + 255) / 256, 256, 0, stream>>>(D, ldd, n, K, nch, planes, Dt);
+    LYS_LAUNCH_CHECK("prep_dict_kernel");
+    if (k <= 5)
+        return (pair == 2) ? launch_tc<5, 2, 1>(X, xfs, xss, n, planes, Dt, nullptr, K, N, k, idx, val, nsel, Z, zss, nullptr, stream)
+                           : launch_tc<5, 1, 1>(X, xfs, xss, n, planes, Dt, nullptr, K, N, k, idx, val, nsel, Z, zss, nullptr, stream);
+    return (pair == 2) ? launch_tc<10, 2, 1>(X, xfs, xss, n, planes, Dt, nullptr, K, N, k, idx, val, nsel, Z, zss, nullptr, stream)
+                       : launch_tc<10, 1, 1>(X, xfs, xss, n, planes, Dt, nullptr, K, N, k, idx, val, nsel, Z, zss, nullptr, stream);
 }
 
 }  // namespace lys

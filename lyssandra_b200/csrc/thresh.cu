@@ -3,8 +3,9 @@
 //            n_nonzero_coefs LARGEST SIGNED correlations of every signal, Z = Alpha there;
 //   'iht'    (:433-446, dispatch :671-690): Z0 = thresh(Alpha), then n_iter times
 //            Z <- Z - eta * D^T (D Z - X), keep the k largest |Z| of every signal.
-// Both are a correlation GEMM (corr_gemm_tc.cu / gemm.cu) followed by a per-signal selection,
-// which is one warp per signal over a shared-memory copy of the signal's row.
+// 'thresh' at the fused kernel's shapes (n <= 64, K in {256,512,768,1024}, k <= 10) runs inside it
+// (bomp_fused.cu, MODE 1: correlations never leave TMEM).  Everything else here is a correlation
+// GEMM (corr_gemm_tc.cu / gemm.cu) followed by a per-signal selection kernel, one warp per signal.
 #include "common.cuh"
 #include "../../include/lyssa_b200.h"
 
@@ -19,6 +20,12 @@ size_t corr_gemm_tc_planes_bytes(int n, int K);
 int corr_gemm_tc_prepare(const float* D, int64_t ldd, int n, int K, void* planes, cudaStream_t stream);
 int corr_gemm_tc(const float* X, int64_t xfs, int64_t xss, const void* planes,
                  int n, int K, int64_t C, float* alpha, cudaStream_t stream);
+
+// 'thresh' inside the fused tcgen05 kernel (bomp_fused.cu, MODE 1); LYS_EUNSUPPORTED for shapes it is not built for
+int thresh_encode_fused(const float* X, int64_t xfs, int64_t xss, const float* D, int64_t ldd,
+                        int n, int K, int64_t N, int k, int32_t* idx, float* val, int32_t* nsel,
+                        float* Z, int64_t zas, int64_t zss, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t thresh_fused_workspace_bytes(int n, int K, int64_t N, int k);
 
 namespace {
 
@@ -102,13 +109,16 @@ select_topk_kernel(const float* __restrict__ alpha, float scale,
 }
 
 // Register variant for K <= 32*IPL <= 1024 and k <= 32 (the shapes the coders are used at).  A lane holds the
-// keys of columns j*32+lane.  Instead of k full passes it (1) takes the k-th largest of the 32 lane maxima as a
-// threshold T — at least k entries are >= T, and every one of the row's k largest is — (2) marks the entries
-// >= T in a per-lane bit mask (a handful per row), and (3) runs the k selection rounds over those candidates
-// only, each lane caching its best candidate and rescanning its mask only after it has won a round.
+// keys of columns j*32+lane.  Nothing in it is a k-deep chain of warp reductions:
+//  (1) T = the k-th largest of the 32 lane maxima, found by ranking them against each other with 31 butterfly
+//      shuffles — at least k entries of the row are >= T, and every one of its k largest is;
+//  (2) entries >= T (a handful per row) are appended to a per-warp candidate list in shared memory;
+//  (3) with at most 32 candidates, lane l ranks candidate l among all of them in the order (key descending,
+//      column ascending) with another 31 butterfly shuffles and, if its rank is below k, writes output slot
+//      `rank` itself.  Rows with more candidates (heavy ties) take k sequential rounds over the masks instead.
 // Same result as select_topk_kernel: descending key, ties to the lower column.
-template <int IPL, bool ABS>
-__global__ void __launch_bounds__(SEL_WARPS * 32)
+template <int IPL, bool ABS, bool PREV>
+__global__ void __launch_bounds__(SEL_WARPS * 32, IPL == 32 ? 3 : 6)
 select_topk_reg_kernel(const float* __restrict__ alpha, float scale,
                        const int32_t* prev_idx, const float* prev_val, int prev_k,
                        int K, int64_t C, int k,
@@ -116,6 +126,9 @@ select_topk_reg_kernel(const float* __restrict__ alpha, float scale,
                        float* __restrict__ Z, int64_t zas, int64_t zss)
 {
     extern __shared__ float srow_all[];
+    __shared__ int cand_cnt[SEL_WARPS];
+    __shared__ int cand_col[SEL_WARPS][32];
+    constexpr int NONE = 0x7fffffff;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpc = blockDim.x >> 5;
     float* srow = srow_all + (size_t)warp * (IPL * 32);
@@ -126,30 +139,24 @@ select_topk_reg_kernel(const float* __restrict__ alpha, float scale,
     for (int64_t i = (int64_t)blockIdx.x * wpc + warp; i < C; i += (int64_t)gridDim.x * wpc) {
         const float* a = alpha + i * K;
         float key[IPL];
-        if (prev_idx) {
-            // stage through shared memory so the previous code can be added by column
 #pragma unroll
-            for (int j = 0; j < IPL; ++j) srow[j * 32 + lane] = ((valid >> j) & 1u) ? scale * __ldcs(a + j * 32 + lane) : 0.f;
-            __syncwarp();
+        for (int j = 0; j < IPL; ++j) key[j] = ((valid >> j) & 1u) ? scale * __ldcs(a + j * 32 + lane) : 0.f;
+        if (lane == 0) cand_cnt[warp] = 0;
+#pragma unroll
+        for (int j = 0; j < IPL; ++j) srow[j * 32 + lane] = key[j];
+        __syncwarp();
+        if (PREV) {
+            // the previous code is added by column through shared memory
             for (int t = lane; t < prev_k; t += 32) {
                 const int p = prev_idx[i * prev_k + t];
                 if (p >= 0) srow[p] += prev_val[i * prev_k + t];
             }
             __syncwarp();
 #pragma unroll
-            for (int j = 0; j < IPL; ++j) {
-                const float v = srow[j * 32 + lane];
-                key[j] = ((valid >> j) & 1u) ? (ABS ? fabsf(v) : v) : -INFINITY;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < IPL; ++j) {
-                const float v = ((valid >> j) & 1u) ? scale * __ldcs(a + j * 32 + lane) : 0.f;
-                srow[j * 32 + lane] = v;
-                key[j] = ((valid >> j) & 1u) ? (ABS ? fabsf(v) : v) : -INFINITY;
-            }
-            __syncwarp();
+            for (int j = 0; j < IPL; ++j) key[j] = srow[j * 32 + lane];
         }
+#pragma unroll
+        for (int j = 0; j < IPL; ++j) key[j] = ((valid >> j) & 1u) ? (ABS ? fabsf(key[j]) : key[j]) : -INFINITY;
         if (Z) {
             float* z = Z + i * zss;
             if (zas == 1 && (K % 4) == 0 && ((reinterpret_cast<uintptr_t>(z) & 15) == 0)) {
@@ -160,55 +167,89 @@ select_topk_reg_kernel(const float* __restrict__ alpha, float scale,
             }
             __syncwarp();
         }
-        float m = key[0];
+        // lane maximum (pairwise tree) and its rank among the 32 lane maxima
+        float t2[IPL];
 #pragma unroll
-        for (int j = 1; j < IPL; ++j) m = fmaxf(m, key[j]);
-        float cur = m, T = -INFINITY;
-        for (int r = 0; r < k; ++r) {
-            T = cur;
+        for (int j = 0; j < IPL; ++j) t2[j] = key[j];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) T = fmaxf(T, __shfl_xor_sync(0xffffffffu, T, o));
-            if (cur == T) cur = -INFINITY;
+        for (int w = IPL / 2; w > 0; w >>= 1)
+#pragma unroll
+            for (int j = 0; j < w; ++j) t2[j] = fmaxf(t2[j], t2[j + w]);
+        const float m = t2[0];
+        int rank = 0;
+#pragma unroll
+        for (int o = 1; o < 32; ++o) {
+            // partner lane^o is below this lane iff the top set bit of o is set in lane
+            const int hb = o >= 16 ? 16 : o >= 8 ? 8 : o >= 4 ? 4 : o >= 2 ? 2 : 1;
+            const float om = __shfl_xor_sync(0xffffffffu, m, o);
+            rank += (om > m || (om == m && (lane & hb))) ? 1 : 0;
         }
+        const unsigned kth = __ballot_sync(0xffffffffu, rank == k - 1);
+        const float T = __shfl_sync(0xffffffffu, m, kth ? __ffs(kth) - 1 : 0);
         uint32_t cm = 0;
 #pragma unroll
         for (int j = 0; j < IPL; ++j) cm |= (key[j] >= T) ? (1u << j) : 0u;
         cm &= valid;
-
-        float lb;
-        int lj;
-        auto rescan = [&]() {
-            lb = -INFINITY;
-            lj = -1;
-            uint32_t mk = cm;
-            while (mk) {
-                const int j = __ffs(mk) - 1;
-                mk &= mk - 1;
-                const float v = srow[j * 32 + lane];
-                const float kk = ABS ? fabsf(v) : v;
-                if (kk > lb || lj < 0) { lb = kk; lj = j; }
-            }
-        };
-        rescan();
-        for (int r = 0; r < k; ++r) {
-            float best = lb;
-            int bc = lj >= 0 ? lj * 32 + lane : 0x7fffffff;
+        for (uint32_t mk = cm; mk; mk &= mk - 1) {
+            const int slot = atomicAdd(&cand_cnt[warp], 1);
+            if (slot < 32) cand_col[warp][slot] = (__ffs(mk) - 1) * 32 + lane;
+        }
+        __syncwarp();
+        const int n = cand_cnt[warp];
+        if (n <= 32) {
+            const int c = lane < n ? cand_col[warp][lane] : NONE;
+            const float v = lane < n ? srow[c] : 0.f;
+            const float kk = lane < n ? (ABS ? fabsf(v) : v) : -INFINITY;
+            int rk = 0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
-                if (oc != 0x7fffffff && (bc == 0x7fffffff || ob > best || (ob == best && oc < bc))) { best = ob; bc = oc; }
+            for (int o = 1; o < 32; ++o) {
+                const float ok = __shfl_xor_sync(0xffffffffu, kk, o);
+                const int oc = __shfl_xor_sync(0xffffffffu, c, o);
+                rk += (oc != NONE && (ok > kk || (ok == kk && oc < c))) ? 1 : 0;
             }
-            if (lane == 0) {
-                const bool ok = bc < K;
-                const float v = ok ? srow[bc] : 0.f;
-                idx[i * k + r] = ok ? bc : -1;
-                val[i * k + r] = v;
-                if (Z && ok) Z[i * zss + (int64_t)bc * zas] = v;
+            if (lane < n && rk < k) {
+                idx[i * k + rk] = c;
+                val[i * k + rk] = v;
+                if (Z) Z[i * zss + (int64_t)c * zas] = v;
             }
-            if (lj >= 0 && bc == lj * 32 + lane) {
-                cm &= ~(1u << lj);
-                rescan();
+            for (int r = n + lane; r < k; r += 32) {                 // only for rows without k finite entries
+                idx[i * k + r] = -1;
+                val[i * k + r] = 0.f;
+            }
+        } else {
+            float lb;
+            int lj;
+            auto rescan = [&]() {
+                lb = -INFINITY;
+                lj = -1;
+                for (uint32_t mk = cm; mk; mk &= mk - 1) {
+                    const int j = __ffs(mk) - 1;
+                    const float v = srow[j * 32 + lane];
+                    const float kk = ABS ? fabsf(v) : v;
+                    if (kk > lb || lj < 0) { lb = kk; lj = j; }
+                }
+            };
+            rescan();
+            for (int r = 0; r < k; ++r) {
+                float best = lb;
+                int bc = lj >= 0 ? lj * 32 + lane : NONE;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+                    if (oc != NONE && (bc == NONE || ob > best || (ob == best && oc < bc))) { best = ob; bc = oc; }
+                }
+                if (lane == 0) {
+                    const bool ok = bc < K;
+                    const float v = ok ? srow[bc] : 0.f;
+                    idx[i * k + r] = ok ? bc : -1;
+                    val[i * k + r] = v;
+                    if (Z && ok) Z[i * zss + (int64_t)bc * zas] = v;
+                }
+                if (lj >= 0 && bc == lj * 32 + lane) {
+                    cm &= ~(1u << lj);
+                    rescan();
+                }
             }
         }
         if (nsel && lane == 0) nsel[i] = k;
@@ -222,13 +263,15 @@ int launch_select_reg(bool use_abs, const float* alpha, float scale, const int32
                       float* Z, int64_t zas, int64_t zss, cudaStream_t stream)
 {
     const size_t smem = (size_t)SEL_WARPS * IPL * 32 * sizeof(float);
-    const int64_t blocks = std::min<int64_t>((C + SEL_WARPS - 1) / SEL_WARPS, (int64_t)sm_count() * 6);
-    if (use_abs)
-        select_topk_reg_kernel<IPL, true><<<(unsigned)blocks, SEL_WARPS * 32, smem, stream>>>(alpha, scale, pidx, pval, pk, K, C, k,
-                                                                                               idx, val, nsel, Z, zas, zss);
-    else
-        select_topk_reg_kernel<IPL, false><<<(unsigned)blocks, SEL_WARPS * 32, smem, stream>>>(alpha, scale, pidx, pval, pk, K, C, k,
-                                                                                                idx, val, nsel, Z, zas, zss);
+    const int64_t blocks = std::min<int64_t>((C + SEL_WARPS - 1) / SEL_WARPS, (int64_t)sm_count() * (IPL == 32 ? 3 : 6));
+#define LYS_SEL_LAUNCH(A, P)                                                                                           \
+    select_topk_reg_kernel<IPL, A, P><<<(unsigned)blocks, SEL_WARPS * 32, smem, stream>>>(alpha, scale, pidx, pval, pk, K, C, k, \
+                                                                                          idx, val, nsel, Z, zas, zss)
+    if (use_abs && pidx) LYS_SEL_LAUNCH(true, true);
+    else if (use_abs) LYS_SEL_LAUNCH(true, false);
+    else if (pidx) LYS_SEL_LAUNCH(false, true);
+    else LYS_SEL_LAUNCH(false, false);
+#undef LYS_SEL_LAUNCH
     LYS_LAUNCH_CHECK("select_topk_reg_kernel");
     return LYS_OK;
 }
@@ -284,7 +327,7 @@ ThreshLayout thresh_layout(int n, int K, int64_t N, bool iht)
         L.resid_ws_bytes = lys_residual_workspace_bytes(n, K, L.chunk);
         off += align_up(L.resid_ws_bytes, 256);
     }
-    L.total = off + 256;
+    L.total = std::max(off + 256, thresh_fused_workspace_bytes(n, K, N, 1));
     return L;
 }
 
@@ -309,6 +352,17 @@ int thresh_common(bool iht, const float* X, int64_t xfs, int64_t xss, const floa
         set_error("%s: workspace %zu B < required %zu B", who, workspace_bytes, L.total);
         return LYS_EWORKSPACE;
     }
+    // correlation, selection (and dense rows) in one kernel when the shape allows it; for 'iht' this is the start Z0
+    bool have_start = false;
+    {
+        const bool final_codes = !iht || n_iter == 0;
+        const int frc = thresh_encode_fused(X, xfs, xss, D, ldd, n, K, N, k, idx, val, nsel, final_codes ? Z : nullptr, zas, zss,
+                                            workspace, workspace_bytes, stream);
+        if (frc != LYS_EUNSUPPORTED) {
+            if (frc != LYS_OK || final_codes) return frc;
+            have_start = true;
+        }
+    }
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
     float* alpha = reinterpret_cast<float*>(ws + L.alpha_off);
     void* planes = ws + L.planes_off;
@@ -330,9 +384,11 @@ int thresh_common(bool iht, const float* X, int64_t xfs, int64_t xss, const floa
         int32_t* cn = nsel ? nsel + s0 : nullptr;
         float* Zc = Z ? Z + s0 * zss : nullptr;
         const bool last0 = !iht || n_iter == 0;
-        if ((rc = corr(Xc, xfs, xss, C))) return rc;
-        if ((rc = launch_select(false, alpha, 1.f, nullptr, nullptr, 0, K, C, k, ci, cv, cn,
-                                last0 ? Zc : nullptr, zas, zss, stream))) return rc;
+        if (!have_start) {
+            if ((rc = corr(Xc, xfs, xss, C))) return rc;
+            if ((rc = launch_select(false, alpha, 1.f, nullptr, nullptr, 0, K, C, k, ci, cv, cn,
+                                    last0 ? Zc : nullptr, zas, zss, stream))) return rc;
+        }
         for (int it = 0; iht && it < n_iter; ++it) {
             // R = X - D Z (the reference keeps D Z - X and subtracts eta * D^T R; same update)
             if ((rc = lys_residual(Xc, xfs, xss, D, ldd, ci, cv, n, K, C, k, R, nullptr,
