@@ -236,6 +236,29 @@ def scspm_images_per_s(dev, n_imgs=128, size=256, reps=3):
     return n_imgs * reps / (e0.elapsed_time(e1) / 1e3), 41 * 41
 
 
+def sibling_coders_ms(dev, n=64, K=1024, N=1 << 20, k=5, reps=3):
+    """'thresh' and 'iht'  on the headline workload's shape: ms per 1M signals, codes stay sparse."""
+    import torch
+    from lyssandra_b200 import engine
+    from oracle import lyssa_oracle as lo
+    X = engine.as_device_matrix(torch.from_numpy(np.ascontiguousarray(lo.synthetic_patches(N, n, seed=21))).to(dev), dev)
+    D = engine.as_dictionary(torch.from_numpy(lo.synthetic_dictionary(K, n, seed=22)).to(dev), dev)
+    out = {}
+    for name, fn in (("thresh", lambda: engine.thresh_encode(X, D, k)),
+                     ("thresh_dense", lambda: engine.thresh_encode(X, D, k, dense=True)),
+                     ("iht_4_iterations", lambda: engine.iht_encode(X, D, k, 0.2, 4))):
+        fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        out[name] = e0.elapsed_time(e1) / reps
+    return out
+
+
 # ----------------------------------------------------------------------------- own arm
 def run_own(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -379,6 +402,13 @@ def run_own(args):
         except Exception as exc:
             spm_note = "failed: %r" % (exc,)
 
+    sib_ms, sib_note = None, None
+    if not args.no_extras and rank == 0:
+        try:
+            sib_ms = sibling_coders_ms(dev)
+        except Exception as exc:
+            sib_note = "failed: %r" % (exc,)
+
     t = torch.tensor([ms, e2e_s * 1e3 / e2e_steps, e2e_sparse_s * 1e3 / e2e_steps, ksvd_ms if ksvd_ms is not None else -1.0],
                      dtype=torch.float64, device=dev)
     if world > 1:
@@ -426,7 +456,9 @@ def run_own(args):
                                           "collective": "none" if world == 1 else "per-atom (n+2)-float all-reduce inside the sweep kernel over peer-mapped NVLink buffers; scalar NCCL all-reduce of the error",
                                           "note": ksvd_note},
                        "scspm_pipeline": {"workload": "128 synthetic 256x256 images (rank 0 only) -> dense SIFT 16x16 / step 6 (1681 descriptors per image) -> Batch-OMP D 128x1024 k=5 -> 3-level max-|z| pooling + l2, images resident on the device",
-                                          "images_per_s": spm_rate, "note": spm_note}},
+                                          "images_per_s": spm_rate, "note": spm_note},
+                       "sibling_coders": {"workload": "'thresh' / 'iht' coders, 1M synthetic patches (rank 0 only), D 64x1024, k=5, eta=0.2, sparse codes out unless noted",
+                                          "ms_per_1M_signals": sib_ms, "note": sib_note}},
         }
         traffic_file = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
         if os.path.isfile(traffic_file):
