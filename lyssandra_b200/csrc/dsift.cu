@@ -8,7 +8,7 @@
 //   3. Lowe normalisation (:146-162): f /= max(|f|, nrml_thres); f = min(f, sift_thres); renormalise the
 //      high-contrast ones.
 // Patch order and positions as in process_image (:106-118): p = a * n_h + b at (h_b, w_a).
-// Bound: L2/SIMT — per patch 128 outputs x 49 non-zero weights, orientation maps are re-read from L2.
+// Bound: L2 — each patch stages 8 x ps x ps map values (overlapping patches re-read them from L2).
 #include "common.cuh"
 
 namespace lys {
@@ -51,25 +51,41 @@ __global__ void dsift_orient_kernel(const float* __restrict__ img, int64_t row_s
     }
 }
 
-// one block of 128 threads per patch: thread = (angle, spatial bin)
-__global__ void dsift_desc_kernel(const float* __restrict__ orient, int H, int W, int ps, int gs, int off_h, int off_w,
-                                  int n_h, int n_w, DsiftParams P, float nrml_thres, float sift_thres,
-                                  float* __restrict__ desc, float* __restrict__ pos)
+// one block of 128 threads per patch.  The patch of the 8 orientation maps (8 x ps x ps floats) is staged in
+// shared memory once; the separable bilinear weighting runs as a horizontal pass (angle, row, column-bin) and a
+// vertical pass (angle, row-bin, column-bin) — same summation order as a direct double loop, 3x fewer
+// multiply-adds and no repeated global reads.  Row pitches are padded by one float against bank conflicts.
+__global__ void __launch_bounds__(kDesc)
+dsift_desc_kernel(const float* __restrict__ orient, int H, int W, int ps, int gs, int off_h, int off_w,
+                  int n_h, int n_w, DsiftParams P, float nrml_thres, float sift_thres,
+                  float* __restrict__ desc, float* __restrict__ pos)
 {
+    extern __shared__ float dsm[];
+    const int pitch = ps + 1;
+    float* smap = dsm;                                   // [angle][row][pitch]
+    float* srow = smap + kAngles * ps * pitch;           // [angle][row][column bin]
+    float* swt = srow + kAngles * ps * kBins;            // [bin][kMaxPs + 1]
     const int p = blockIdx.x;
     const int a = p / n_h, b = p % n_h;                                       // :107-109 meshgrid order
     const int h0 = off_h + b * gs, w0 = off_w + a * gs;
     const int t = threadIdx.x, ang = t / kSamples, bin = t % kSamples, bi = bin / kBins, bj = bin % kBins;
-    const float* map = orient + (int64_t)ang * H * W;
-    float acc = 0.f;
-    for (int i = 0; i < ps; ++i) {
-        const float wi = P.wt[bi * kMaxPs + i];
-        if (wi == 0.f) continue;
-        const float* rowp = map + (int64_t)(h0 + i) * W + w0;
-        float s = 0.f;
-        for (int j = 0; j < ps; ++j) s = fmaf(P.wt[bj * kMaxPs + j], __ldg(rowp + j), s);
-        acc = fmaf(wi, s, acc);
+    for (int e = t; e < kAngles * ps * ps; e += kDesc) {
+        const int j = e % ps, i = (e / ps) % ps, g = e / (ps * ps);
+        smap[(g * ps + i) * pitch + j] = __ldg(orient + ((int64_t)g * H + (h0 + i)) * W + w0 + j);
     }
+    if (t < kBins * kMaxPs) swt[(t / kMaxPs) * (kMaxPs + 1) + (t % kMaxPs)] = P.wt[t];
+    __syncthreads();
+    for (int o = t; o < kAngles * ps * kBins; o += kDesc) {
+        const int cb = o % kBins, gi = o / kBins;                             // gi = angle * ps + row
+        const float* r = smap + gi * pitch;
+        const float* w = swt + cb * (kMaxPs + 1);
+        float sacc = 0.f;
+        for (int j = 0; j < ps; ++j) sacc = fmaf(w[j], r[j], sacc);
+        srow[o] = sacc;
+    }
+    __syncthreads();
+    float acc = 0.f;
+    for (int i = 0; i < ps; ++i) acc = fmaf(swt[bi * (kMaxPs + 1) + i], srow[(ang * ps + i) * kBins + bj], acc);
     // ---- :146-162
     __shared__ float red[4];
     __shared__ float bc;
@@ -134,7 +150,9 @@ extern "C" int lys_dsift(const float* img, int64_t row_stride, int H, int W, int
     dim3 blk(32, 8), grd((W + 31) / 32, (H + 7) / 8);
     dsift_orient_kernel<<<grd, blk, 0, stream>>>(img, row_stride, H, W, P, orient);
     LYS_LAUNCH_CHECK("dsift_orient_kernel");
-    dsift_desc_kernel<<<(unsigned)(n_h * n_w), kDesc, 0, stream>>>(orient, H, W, patch_size, grid_spacing, off_h, off_w, n_h, n_w, P,
+    const size_t desc_smem = ((size_t)kAngles * patch_size * (patch_size + 1) + (size_t)kAngles * patch_size * kBins +
+                              (size_t)kBins * (kMaxPs + 1)) * sizeof(float);
+    dsift_desc_kernel<<<(unsigned)(n_h * n_w), kDesc, desc_smem, stream>>>(orient, H, W, patch_size, grid_spacing, off_h, off_w, n_h, n_w, P,
                                                                   nrml_thres, sift_thres, desc, pos);
     LYS_LAUNCH_CHECK("dsift_desc_kernel");
     return LYS_OK;

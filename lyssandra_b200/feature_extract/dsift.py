@@ -54,10 +54,9 @@ class DsiftExtractor(object):
         self._gw = np.ascontiguousarray(gw, dtype=np.float32)
         self._wt = np.ascontiguousarray(bin_weights(self.ps), dtype=np.float32)
 
-    def process_image(self, image, positionNormalize=False, device=None):
-        """-> (feat_arr (P, 128) CUDA tensor, positions (2, P) CUDA tensor), dsift.py:75-118"""
-        engine._require_cuda()
-        lib = nat.load()
+    @staticmethod
+    def _device_image(image, device=None):
+        """grayscale float32 contiguous CUDA tensor of one image (:92-94)"""
         if torch.is_tensor(image):
             img = image
         else:
@@ -66,12 +65,56 @@ class DsiftExtractor(object):
             img = img.to(torch.float64).mean(dim=2)                      # :92-94 grayscale
         if device is None:
             device = img.device if img.is_cuda else torch.device("cuda", torch.cuda.current_device())
-        img = img.to(device=device, dtype=torch.float32).contiguous()
-        H, W = int(img.shape[0]), int(img.shape[1])
+        if img.is_cuda and img.dtype == torch.float32 and img.device == device and img.is_contiguous():
+            return img
+        return img.to(device=device, dtype=torch.float32).contiguous()
+
+    def _grid(self, lib, H, W):
         nh, nw, oh, ow = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         nat.check(lib.lys_dsift_grid(H, W, int(self.gs), int(self.ps), ctypes.byref(nh), ctypes.byref(nw),
                                      ctypes.byref(oh), ctypes.byref(ow)))
-        P = nh.value * nw.value
+        return nh.value, nw.value
+
+    def process_images(self, images, device=None):
+        """Descriptors of a list of images into ONE signal-major buffer (what the ScSPM encoder consumes):
+        -> desc (sum P_i, 128), pos (sum P_i, 2) top-left (row, col), counts [P_i], sizes [(H_i, W_i)].
+        One pair of kernel launches per image, no per-image allocations or concatenation."""
+        engine._require_cuda()
+        lib = nat.load()
+        imgs = [self._device_image(im, device) for im in images]
+        if not imgs:
+            raise ValueError("no images")
+        dev = imgs[0].device
+        sizes = [(int(t.shape[0]), int(t.shape[1])) for t in imgs]
+        counts = []
+        for H, W in sizes:
+            nh, nw = self._grid(lib, H, W)
+            counts.append(nh * nw)
+        total = int(sum(counts))
+        desc = torch.empty((total, n_samples * n_angles), dtype=torch.float32, device=dev)
+        pos = torch.empty((total, 2), dtype=torch.float32, device=dev)
+        ws = engine.workspace(dev, max(lib.lys_dsift_workspace_bytes(H, W) for H, W in set(sizes)), tag="dsift")
+        dptr, pptr, wptr, wbytes = desc.data_ptr(), pos.data_ptr(), engine._ptr(ws), ws.numel()
+        gs, ps, nt, st = int(self.gs), int(self.ps), float(self.nrml_thres), float(self.sift_thres)
+        gh, gw, wt = self._gh.ctypes.data, self._gw.ctypes.data, self._wt.ctypes.data
+        off = 0
+        with torch.cuda.device(dev):
+            stream = engine._stream_ptr(dev)
+            for t, (H, W), c in zip(imgs, sizes, counts):
+                nat.check(lib.lys_dsift(t.data_ptr(), t.stride(0), H, W, gs, ps, nt, st, gh, gw, wt,
+                                        dptr + off * 512, pptr + off * 8, wptr, wbytes, stream))
+                off += c
+        return desc, pos, counts, sizes
+
+    def process_image(self, image, positionNormalize=False, device=None):
+        """-> (feat_arr (P, 128) CUDA tensor, positions (2, P) CUDA tensor), dsift.py:75-118"""
+        engine._require_cuda()
+        lib = nat.load()
+        img = self._device_image(image, device)
+        device = img.device
+        H, W = int(img.shape[0]), int(img.shape[1])
+        nh, nw = self._grid(lib, H, W)
+        P = nh * nw
         desc = torch.empty((P, n_samples * n_angles), dtype=torch.float32, device=device)
         pos = torch.empty((P, 2), dtype=torch.float32, device=device)
         wsb = lib.lys_dsift_workspace_bytes(H, W)

@@ -36,6 +36,13 @@ class dsift_extractor(object):
         dsift_patches, pos = self.extractor.process_image(img, positionNormalize=False)
         return dsift_patches.t(), pos.t()
 
+    def extract_batch(self, imgs):
+        """all images of a call at once: descriptors (128, sum P_i) as a view of one signal-major buffer,
+        positions (sum P_i, 2), owner image of every patch (host int32), image sizes"""
+        desc, pos, counts, sizes = self.extractor.process_images(imgs)
+        owner = np.repeat(np.arange(len(counts), dtype=np.int32), counts)
+        return desc.t(), pos, torch.from_numpy(owner), sizes
+
 
 def spm_pool(codes, patch_img, patch_pos, patch_size, img_hw, levels=(1, 2, 4), pooling_operator=None, normalizer=None):
     """Pool sparse codes over the spatial pyramid of every image.
@@ -82,6 +89,13 @@ class sc_spm_extractor(object):
     def encode(self, imgs, dictionary):
         engine._require_cuda()
         psize = self.feature_extractor.patch_size
+        if hasattr(self.feature_extractor, "extract_batch"):             # device producer: no per-image tensors
+            X, pos, owner, hw = self.feature_extractor.extract_batch(imgs)
+            D = engine.as_dictionary(dictionary, X.device)
+            codes = self.sparse_coder.encode_sparse(X, D)
+            F = spm_pool(codes, owner, pos, psize, torch.tensor(hw, dtype=torch.int32),
+                         self.levels, self.pooling_operator, self.normalizer)
+            return F.t()
         descs, poss, owner, hw = [], [], [], []
         for i, img in enumerate(imgs):                                   # :55-63 (producer side, per image)
             desc, pos = self.feature_extractor.extract(img)
