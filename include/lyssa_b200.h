@@ -94,7 +94,7 @@ LYS_API int lys_bomp_encode(const float* X, int64_t x_feat_stride, int64_t x_sig
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* The correlation GEMM alone (test/bring-up hook): alpha (C,K) row-major = X^T D.
- * impl: 0 = what lys_bomp_encode uses, 1 = fp32 SIMT, 2 = tcgen05 bf16x3 (n = 64, K % 256 == 0). */
+ * impl: 0 = what lys_bomp_encode uses, 1 = fp32 SIMT, 2 = tcgen05 bf16x3 (n = 64 or 128, K % 256 == 0). */
 LYS_API int lys_corr_gemm(const float* X, int64_t x_feat_stride, int64_t x_sig_stride,
                           const float* D, int64_t ldd, int n, int K, int64_t C, float* alpha,
                           int impl, void* stream);

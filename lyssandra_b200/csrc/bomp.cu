@@ -60,7 +60,7 @@ bool profile_begin(cudaStream_t st, const char* name, cudaEvent_t* stop_out)
 
 namespace {
 
-constexpr int NF_MAX_HOOK = 64;
+constexpr int NF_MAX_HOOK = 128;
 
 // signals per correlation chunk: the (chunk x K) fp32 Alpha tile is written by the GEMM kernel
 // and read once by the greedy kernel.  Measured on B200 (profiles/README.md): per-launch fixed
@@ -180,7 +180,8 @@ extern "C" int lys_bomp_launch_count(int n, int K, int64_t N, int k)
     int fused = bomp_fused_launch_count(n, K, N, k);
     if (fused > 0) return fused;
     const int64_t chunk = generic_chunk(K, N);
-    return (int)(2 * ((N + chunk - 1) / chunk)) + (corr_gemm_tc_supported(n, K) ? 1 : 0);
+    const int halves = corr_gemm_tc_supported(n, K) ? (n > 64 ? 2 : 1) : 0;      // tensor-core GEMM launches per chunk
+    return (int)(((halves ? halves : 1) + 1) * ((N + chunk - 1) / chunk)) + halves;
 }
 
 extern "C" int lys_profile_enable(int on)
@@ -217,7 +218,7 @@ extern "C" int lys_corr_gemm(const float* X, int64_t xfs, int64_t xss, const flo
     if (impl == 0) impl = corr_gemm_tc_supported(n, K) ? 2 : 1;
     if (impl == 1) return sgemm_strided(X, xss, xfs, D, ldd, 1, alpha, K, 1, C, K, n, (cudaStream_t)stream);
     if (impl == 2) {
-        if (!corr_gemm_tc_supported(n, K)) { set_error("lys_corr_gemm: tcgen05 path needs n=64, K multiple of 256"); return LYS_EUNSUPPORTED; }
+        if (!corr_gemm_tc_supported(n, K)) { set_error("lys_corr_gemm: tcgen05 path needs n=64 or 128, K multiple of 256"); return LYS_EUNSUPPORTED; }
         static void* hook_planes[64] = {nullptr};          // bring-up hook only: cached per device, never freed
         int dev = 0;
         LYS_CUDA(cudaGetDevice(&dev));

@@ -134,7 +134,7 @@ __device__ __forceinline__ void store_chunk(unsigned char* plane0, int plane_byt
 __global__ void __launch_bounds__(THREADS, 1)
 corr_gemm_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss,
                     const uint4* __restrict__ planes /* per 256-atom slice: 3 planes in smem layout */,
-                    int K, int64_t C, float* __restrict__ alpha)
+                    int K, int64_t C, float* __restrict__ alpha, int accumulate)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sB = smem;
@@ -253,6 +253,16 @@ corr_gemm_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss,
                 TMEM_LD_32x32b_x32(taddr + c * 32, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (sig < C) {
+                    if (accumulate) {                         // second 64-feature half of a 128-feature product
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 o = *reinterpret_cast<const float4*>(out + c * 32 + q * 4);
+                            r[4 * q] = __float_as_uint(o.x + __uint_as_float(r[4 * q]));
+                            r[4 * q + 1] = __float_as_uint(o.y + __uint_as_float(r[4 * q + 1]));
+                            r[4 * q + 2] = __float_as_uint(o.z + __uint_as_float(r[4 * q + 2]));
+                            r[4 * q + 3] = __float_as_uint(o.w + __uint_as_float(r[4 * q + 3]));
+                        }
+                    }
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
                         *reinterpret_cast<uint4*>(out + c * 32 + q * 4) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
@@ -285,19 +295,25 @@ __global__ void split_dict_planes_kernel(const float* __restrict__ D, int64_t ld
 
 }  // namespace
 
+// n = 64, or n = 128 as two 64-feature halves: the second launch adds its product to the first one's Alpha
 bool corr_gemm_tc_supported(int n, int K)
 {
-    return n == NF && K >= TN && (K % TN) == 0 && K <= LYS_MAX_ATOMS;
+    return (n == NF || n == 2 * NF) && K >= TN && (K % TN) == 0 && K <= LYS_MAX_ATOMS;
 }
 
-size_t corr_gemm_tc_planes_bytes(int n, int K) { return corr_gemm_tc_supported(n, K) ? (size_t)(K / TN) * SMEM_B : 0; }
+static size_t half_planes_bytes(int K) { return (size_t)(K / TN) * SMEM_B; }
+
+size_t corr_gemm_tc_planes_bytes(int n, int K) { return corr_gemm_tc_supported(n, K) ? (size_t)(n / NF) * half_planes_bytes(K) : 0; }
 
 int corr_gemm_tc_prepare(const float* D, int64_t ldd, int n, int K, void* planes, cudaStream_t stream)
 {
     if (!corr_gemm_tc_supported(n, K)) return LYS_EUNSUPPORTED;
     const int items = K * (NF / 8);
-    split_dict_planes_kernel<<<(items + 255) / 256, 256, 0, stream>>>(D, ldd, K, reinterpret_cast<unsigned char*>(planes));
-    LYS_LAUNCH_CHECK("split_dict_planes_kernel");
+    for (int h = 0; h < n / NF; ++h) {
+        split_dict_planes_kernel<<<(items + 255) / 256, 256, 0, stream>>>(D + (int64_t)h * NF * ldd, ldd, K,
+                                                                          reinterpret_cast<unsigned char*>(planes) + h * half_planes_bytes(K));
+        LYS_LAUNCH_CHECK("split_dict_planes_kernel");
+    }
     return LYS_OK;
 }
 
@@ -317,8 +333,11 @@ int corr_gemm_tc(const float* X, int64_t xfs, int64_t xss, const void* planes,
     int groups = sm_count() / n_slices;
     if (groups < 1) groups = 1;
     if ((int64_t)groups > n_tiles) groups = (int)n_tiles;
-    corr_gemm_tc_kernel<<<groups * n_slices, THREADS, SMEM_TOTAL, stream>>>(X, xfs, xss, reinterpret_cast<const uint4*>(planes), K, C, alpha);
-    LYS_LAUNCH_CHECK("corr_gemm_tc_kernel");
+    for (int h = 0; h < n / NF; ++h) {
+        const uint4* pl = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(planes) + h * half_planes_bytes(K));
+        corr_gemm_tc_kernel<<<groups * n_slices, THREADS, SMEM_TOTAL, stream>>>(X + (int64_t)h * NF * xfs, xfs, xss, pl, K, C, alpha, h);
+        LYS_LAUNCH_CHECK("corr_gemm_tc_kernel");
+    }
     return LYS_OK;
 }
 

@@ -14,10 +14,11 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.mark.parametrize("K,C", [(256, 1000), (1024, 4099), (2048, 777), (512, 128), (1024, 1)])
-def test_tcgen05_gemm_is_fp32_faithful(K, C):
+@pytest.mark.parametrize("n,K,C", [(64, 256, 1000), (64, 1024, 4099), (64, 2048, 777), (64, 512, 128), (64, 1024, 1),
+                                   (128, 1024, 3001), (128, 2048, 515)])        # n = 128: two accumulated 64-feature halves
+def test_tcgen05_gemm_is_fp32_faithful(n, K, C):
     lib = _native.load()
-    Xh = np.ascontiguousarray(lo.synthetic_patches(C, 64, seed=3)); Dh = lo.synthetic_dictionary(K, 64, seed=4)
+    Xh = np.ascontiguousarray(lo.synthetic_patches(C, n, seed=3)); Dh = lo.synthetic_dictionary(K, n, seed=4)
     ref = Xh.astype(np.float64).T @ Dh.astype(np.float64)
     scale = np.linalg.norm(Xh.astype(np.float64), axis=0)[:, None]         # |x| |d|, |d| = 1
     X = torch.from_numpy(Xh).to(DEV); D = torch.from_numpy(Dh).to(DEV)
@@ -25,7 +26,7 @@ def test_tcgen05_gemm_is_fp32_faithful(K, C):
     for impl in (1, 2):
         for Xv in (X, X.t().contiguous().t()):                            # feature-major and signal-major
             out = torch.full((C, K), float("nan"), device=DEV)
-            _native.check(lib.lys_corr_gemm(Xv.data_ptr(), Xv.stride(0), Xv.stride(1), D.data_ptr(), K, 64, K, C,
+            _native.check(lib.lys_corr_gemm(Xv.data_ptr(), Xv.stride(0), Xv.stride(1), D.data_ptr(), K, n, K, C,
                                             out.data_ptr(), impl, None))
             torch.cuda.synchronize()
             o = out.cpu().numpy().astype(np.float64)
