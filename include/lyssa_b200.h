@@ -230,6 +230,12 @@ LYS_API int lys_dsift_grid(int H, int W, int grid_spacing, int patch_size, int* 
 LYS_API int lys_dsift(const float* img, int64_t row_stride, int H, int W, int grid_spacing, int patch_size,
                       float nrml_thres, float sift_thres, const float* gh25, const float* gw25, const float* bin_weights,
                       float* desc, float* pos, void* workspace, size_t workspace_bytes, void* stream);
+/* Same for n_imgs images of ONE size: `imgs` is a HOST array of device pointers; descriptors / positions of image i
+ * land at desc + i*P*128, pos + i*P*2 (P = n_h*n_w).  One pair of launches per 128 images; the workspace holds the
+ * orientation maps of as many images as fit (>= lys_dsift_workspace_bytes(H, W), ideally n_imgs times that). */
+LYS_API int lys_dsift_batch(const float* const* imgs, int n_imgs, int64_t row_stride, int H, int W, int grid_spacing, int patch_size,
+                    float nrml_thres, float sift_thres, const float* gh25, const float* gw25, const float* bin_weights,
+                    float* desc, float* pos, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- multi-GPU: peer-mapped exchange buffers for the sweep's per-atom all-reduce ---------
  * One process per GPU.  Each rank creates a comm (allocates its exchange buffer), exports

@@ -58,6 +58,8 @@ SIGNATURES = {
                                ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "lys_dsift": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_int, ctypes.c_float, ctypes.c_float, c_vp, c_vp, c_vp,
                           c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "lys_dsift_batch": (c_int, [c_vp, c_int, c_i64, c_int, c_int, c_int, c_int, ctypes.c_float, ctypes.c_float, c_vp, c_vp, c_vp,
+                                c_vp, c_vp, c_vp, c_sz, c_vp]),
     "lys_comm_create": (c_int, [c_int, c_int, ctypes.POINTER(c_vp)]),
     "lys_comm_export": (c_int, [c_vp, c_vp]),
     "lys_comm_connect": (c_int, [c_vp, c_vp]),

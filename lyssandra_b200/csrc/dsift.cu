@@ -10,6 +10,7 @@
 // Patch order and positions as in process_image (:106-118): p = a * n_h + b at (h_b, w_a).
 // Bound: L2 — each patch stages 8 x ps x ps map values (overlapping patches re-read them from L2).
 #include "common.cuh"
+#include <algorithm>
 
 namespace lys {
 namespace {
@@ -22,11 +23,19 @@ struct DsiftParams {
     float wt[kBins * kMaxPs];        // bilinear bin weights w[bin][pixel] (:57-73, separable factor)
 };
 
-__global__ void dsift_orient_kernel(const float* __restrict__ img, int64_t row_stride, int H, int W, DsiftParams P,
-                                    float* __restrict__ orient)
+constexpr int kMaxBatch = 128;       // images of one size per launch (their pointers travel as a kernel parameter)
+struct DsiftBatch {
+    const float* img[kMaxBatch];
+};
+
+// blockIdx.z = image of the batch; orientation maps of image z at orient + z * 8 * H * W
+__global__ void dsift_orient_kernel(DsiftBatch B, int64_t row_stride, int H, int W, DsiftParams P,
+                                    float* __restrict__ orient_all)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
+    const float* __restrict__ img = B.img[blockIdx.z];
+    float* __restrict__ orient = orient_all + (size_t)blockIdx.z * kAngles * H * W;
     float ih = 0.f, iw = 0.f;
 #pragma unroll
     for (int a = 0; a < 5; ++a) {
@@ -55,12 +64,18 @@ __global__ void dsift_orient_kernel(const float* __restrict__ img, int64_t row_s
 // shared memory once; the separable bilinear weighting runs as a horizontal pass (angle, row, column-bin) and a
 // vertical pass (angle, row-bin, column-bin) — same summation order as a direct double loop, 3x fewer
 // multiply-adds and no repeated global reads.  Row pitches are padded by one float against bank conflicts.
+// blockIdx.y = image of the batch.  PS > 0 fixes the patch size at compile time (16: the reference's default use).
+template <int PS>
 __global__ void __launch_bounds__(kDesc)
-dsift_desc_kernel(const float* __restrict__ orient, int H, int W, int ps, int gs, int off_h, int off_w,
+dsift_desc_kernel(const float* __restrict__ orient_all, int H, int W, int ps_rt, int gs, int off_h, int off_w,
                   int n_h, int n_w, DsiftParams P, float nrml_thres, float sift_thres,
-                  float* __restrict__ desc, float* __restrict__ pos)
+                  float* __restrict__ desc_all, float* __restrict__ pos_all)
 {
     extern __shared__ float dsm[];
+    const int ps = PS > 0 ? PS : ps_rt;
+    const float* __restrict__ orient = orient_all + (size_t)blockIdx.y * kAngles * H * W;
+    float* __restrict__ desc = desc_all + (size_t)blockIdx.y * n_h * n_w * kDesc;
+    float* __restrict__ pos = pos_all + (size_t)blockIdx.y * n_h * n_w * 2;
     const int pitch = ps + 1;
     float* smap = dsm;                                   // [angle][row][pitch]
     float* srow = smap + kAngles * ps * pitch;           // [angle][row][column bin]
@@ -80,11 +95,13 @@ dsift_desc_kernel(const float* __restrict__ orient, int H, int W, int ps, int gs
         const float* r = smap + gi * pitch;
         const float* w = swt + cb * (kMaxPs + 1);
         float sacc = 0.f;
+#pragma unroll
         for (int j = 0; j < ps; ++j) sacc = fmaf(w[j], r[j], sacc);
         srow[o] = sacc;
     }
     __syncthreads();
     float acc = 0.f;
+#pragma unroll
     for (int i = 0; i < ps; ++i) acc = fmaf(swt[bi * (kMaxPs + 1) + i], srow[(ang * ps + i) * kBins + bj], acc);
     // ---- :146-162
     __shared__ float red[4];
@@ -131,29 +148,67 @@ extern "C" int lys_dsift_grid(int H, int W, int grid_spacing, int patch_size, in
     return LYS_OK;
 }
 
-extern "C" int lys_dsift(const float* img, int64_t row_stride, int H, int W, int grid_spacing, int patch_size,
-                         float nrml_thres, float sift_thres, const float* gh25, const float* gw25, const float* bin_weights,
-                         float* desc, float* pos, void* workspace, size_t workspace_bytes, void* stream_)
+namespace lys {
+namespace {
+int dsift_run(const float* const* imgs, int n_imgs, int64_t row_stride, int H, int W, int grid_spacing, int patch_size,
+              float nrml_thres, float sift_thres, const float* gh25, const float* gw25, const float* bin_weights,
+              float* desc, float* pos, void* workspace, size_t workspace_bytes, cudaStream_t stream, const char* who)
 {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    LYS_CHECK_ARG(img && gh25 && gw25 && bin_weights && desc && pos && workspace, "lys_dsift: null pointer");
+    LYS_CHECK_ARG(imgs && n_imgs >= 1 && gh25 && gw25 && bin_weights && desc && pos && workspace, "%s: null pointer", who);
     int n_h, n_w, off_h, off_w;
     int rc = lys_dsift_grid(H, W, grid_spacing, patch_size, &n_h, &n_w, &off_h, &off_w);
     if (rc) return rc;
-    if (workspace_bytes < lys_dsift_workspace_bytes(H, W)) { set_error("lys_dsift: workspace too small"); return LYS_EWORKSPACE; }
+    const size_t per_img = lys_dsift_workspace_bytes(H, W);
+    if (workspace_bytes < per_img) { set_error("%s: workspace too small", who); return LYS_EWORKSPACE; }
     DsiftParams P;
     for (int i = 0; i < 25; ++i) { P.gh[i] = gh25[i]; P.gw[i] = gw25[i]; }
     for (int i = 0; i < kAngles; ++i) { const double ang = i * 2.0 * 3.14159265358979323846 / kAngles; P.ca[i] = (float)cos(ang); P.sa[i] = (float)sin(ang); }
     for (int b = 0; b < kBins; ++b)
         for (int i = 0; i < kMaxPs; ++i) P.wt[b * kMaxPs + i] = (i < patch_size) ? bin_weights[b * patch_size + i] : 0.f;
     float* orient = reinterpret_cast<float*>(workspace);
-    dim3 blk(32, 8), grd((W + 31) / 32, (H + 7) / 8);
-    dsift_orient_kernel<<<grd, blk, 0, stream>>>(img, row_stride, H, W, P, orient);
-    LYS_LAUNCH_CHECK("dsift_orient_kernel");
+    const int per_launch = (int)std::min<size_t>(kMaxBatch, workspace_bytes / per_img);
     const size_t desc_smem = ((size_t)kAngles * patch_size * (patch_size + 1) + (size_t)kAngles * patch_size * kBins +
                               (size_t)kBins * (kMaxPs + 1)) * sizeof(float);
-    dsift_desc_kernel<<<(unsigned)(n_h * n_w), kDesc, desc_smem, stream>>>(orient, H, W, patch_size, grid_spacing, off_h, off_w, n_h, n_w, P,
-                                                                  nrml_thres, sift_thres, desc, pos);
-    LYS_LAUNCH_CHECK("dsift_desc_kernel");
+    const size_t n_patch = (size_t)n_h * n_w;
+    for (int i0 = 0; i0 < n_imgs; i0 += per_launch) {
+        const int nb = std::min(per_launch, n_imgs - i0);
+        DsiftBatch B;
+        for (int i = 0; i < nb; ++i) {
+            LYS_CHECK_ARG(imgs[i0 + i] != nullptr, "%s: null image", who);
+            B.img[i] = imgs[i0 + i];
+        }
+        dim3 blk(32, 8), grd((W + 31) / 32, (H + 7) / 8, nb);
+        dsift_orient_kernel<<<grd, blk, 0, stream>>>(B, row_stride, H, W, P, orient);
+        LYS_LAUNCH_CHECK("dsift_orient_kernel");
+        dim3 dgrd((unsigned)n_patch, nb);
+        float* d0 = desc + (size_t)i0 * n_patch * kDesc;
+        float* p0 = pos + (size_t)i0 * n_patch * 2;
+        if (patch_size == 16)
+            dsift_desc_kernel<16><<<dgrd, kDesc, desc_smem, stream>>>(orient, H, W, patch_size, grid_spacing, off_h, off_w, n_h, n_w, P,
+                                                                      nrml_thres, sift_thres, d0, p0);
+        else
+            dsift_desc_kernel<0><<<dgrd, kDesc, desc_smem, stream>>>(orient, H, W, patch_size, grid_spacing, off_h, off_w, n_h, n_w, P,
+                                                                     nrml_thres, sift_thres, d0, p0);
+        LYS_LAUNCH_CHECK("dsift_desc_kernel");
+    }
     return LYS_OK;
+}
+}  // namespace
+}  // namespace lys
+
+extern "C" int lys_dsift(const float* img, int64_t row_stride, int H, int W, int grid_spacing, int patch_size,
+                         float nrml_thres, float sift_thres, const float* gh25, const float* gw25, const float* bin_weights,
+                         float* desc, float* pos, void* workspace, size_t workspace_bytes, void* stream_)
+{
+    const float* one[1] = {img};
+    return dsift_run(one, 1, row_stride, H, W, grid_spacing, patch_size, nrml_thres, sift_thres, gh25, gw25, bin_weights,
+                     desc, pos, workspace, workspace_bytes, (cudaStream_t)stream_, "lys_dsift");
+}
+
+extern "C" int lys_dsift_batch(const float* const* imgs, int n_imgs, int64_t row_stride, int H, int W, int grid_spacing, int patch_size,
+                               float nrml_thres, float sift_thres, const float* gh25, const float* gw25, const float* bin_weights,
+                               float* desc, float* pos, void* workspace, size_t workspace_bytes, void* stream_)
+{
+    return dsift_run(imgs, n_imgs, row_stride, H, W, grid_spacing, patch_size, nrml_thres, sift_thres, gh25, gw25, bin_weights,
+                     desc, pos, workspace, workspace_bytes, (cudaStream_t)stream_, "lys_dsift_batch");
 }

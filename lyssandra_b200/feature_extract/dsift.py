@@ -78,7 +78,7 @@ class DsiftExtractor(object):
     def process_images(self, images, device=None):
         """Descriptors of a list of images into ONE signal-major buffer (what the ScSPM encoder consumes):
         -> desc (sum P_i, 128), pos (sum P_i, 2) top-left (row, col), counts [P_i], sizes [(H_i, W_i)].
-        One pair of kernel launches per image, no per-image allocations or concatenation."""
+        One pair of kernel launches per run of same-sized images, no per-image allocations or concatenation."""
         engine._require_cuda()
         lib = nat.load()
         imgs = [self._device_image(im, device) for im in images]
@@ -93,17 +93,31 @@ class DsiftExtractor(object):
         total = int(sum(counts))
         desc = torch.empty((total, n_samples * n_angles), dtype=torch.float32, device=dev)
         pos = torch.empty((total, 2), dtype=torch.float32, device=dev)
-        ws = engine.workspace(dev, max(lib.lys_dsift_workspace_bytes(H, W) for H, W in set(sizes)), tag="dsift")
+        # runs of consecutive images of one size and row stride go through ONE pair of launches
+        runs, i = [], 0
+        while i < len(imgs):
+            j = i + 1
+            while j < len(imgs) and sizes[j] == sizes[i] and imgs[j].stride(0) == imgs[i].stride(0):
+                j += 1
+            runs.append((i, j))
+            i = j
+        def ws_need(a, b):                                   # orientation maps of a whole run, capped at 2 GB
+            one = lib.lys_dsift_workspace_bytes(sizes[a][0], sizes[a][1])
+            return one * max(1, min(b - a, 128, (2 << 30) // max(one, 1)))
+        wsb = max(ws_need(a, b) for a, b in runs)
+        ws = engine.workspace(dev, wsb, tag="dsift")
         dptr, pptr, wptr, wbytes = desc.data_ptr(), pos.data_ptr(), engine._ptr(ws), ws.numel()
         gs, ps, nt, st = int(self.gs), int(self.ps), float(self.nrml_thres), float(self.sift_thres)
         gh, gw, wt = self._gh.ctypes.data, self._gw.ctypes.data, self._wt.ctypes.data
         off = 0
         with torch.cuda.device(dev):
             stream = engine._stream_ptr(dev)
-            for t, (H, W), c in zip(imgs, sizes, counts):
-                nat.check(lib.lys_dsift(t.data_ptr(), t.stride(0), H, W, gs, ps, nt, st, gh, gw, wt,
-                                        dptr + off * 512, pptr + off * 8, wptr, wbytes, stream))
-                off += c
+            for a, b in runs:
+                H, W = sizes[a]
+                ptrs = (ctypes.c_void_p * (b - a))(*[imgs[q].data_ptr() for q in range(a, b)])
+                nat.check(lib.lys_dsift_batch(ptrs, b - a, imgs[a].stride(0), H, W, gs, ps, nt, st, gh, gw, wt,
+                                              dptr + off * 512, pptr + off * 8, wptr, wbytes, stream))
+                off += sum(counts[a:b])
         return desc, pos, counts, sizes
 
     def process_image(self, image, positionNormalize=False, device=None):

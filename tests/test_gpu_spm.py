@@ -87,3 +87,21 @@ def test_dsift_seeded_and_scspm_pipeline():
     assert Z.shape == Zo.shape
     bad = np.abs(Z - Zo) > 1e-4 * np.max(np.abs(Zo))
     assert bad.mean() < 5e-3, bad.mean()             # a flipped near-tie support moves a few pooled entries
+
+
+@pytest.mark.parametrize("ps,gs", [(16, 6), (8, 4), (12, 5)])
+def test_dsift_batched_launch_equals_per_image(ps, gs):
+    """lys_dsift_batch over runs of same-sized images writes exactly what per-image lys_dsift calls write
+    (runs here: 3 x (40,52), 1 x (33,41), 2 x (40,52)); ps = 16 takes the compile-time-sized kernel"""
+    import torch
+    from lyssandra_b200.feature_extract.dsift import DsiftExtractor
+    sizes = ((40, 52), (40, 52), (40, 52), (33, 41), (40, 52), (40, 52))
+    imgs = [torch.from_numpy((im * 255.0).astype(np.float32)).to("cuda:0") for im in lo.synthetic_images(6, seed=51, sizes=sizes)]
+    ex = DsiftExtractor(grid_spacing=gs, patch_size=ps)
+    desc, pos, counts, hw = ex.process_images(imgs)
+    assert [tuple(s) for s in hw] == list(sizes) and desc.shape[0] == sum(counts)
+    off = 0
+    for im, c in zip(imgs, counts):
+        d1, p1 = ex.process_image(im)
+        assert torch.equal(desc[off:off + c], d1) and torch.equal(pos[off:off + c], p1.t())
+        off += c
