@@ -236,6 +236,36 @@ def scspm_images_per_s(dev, n_imgs=128, size=256, reps=3):
     return n_imgs * reps / (e0.elapsed_time(e1) / 1e3), 41 * 41
 
 
+def odl_minibatch_ms(dev, n=128, K=2048, k=5, b=4096):
+    """One ODL minibatch in the shape of BASELINE cfg4 (SIFT-like 128-d descriptors, D 128x2048, minibatch 4096):
+    encode -> A,B accumulation (beta = 0.9) -> dictionary update; median of 8 minibatches, stage times by CUDA events."""
+    import torch
+    from lyssandra_b200 import engine
+    from lyssandra_b200.sparse_coding import sparse_encoder
+    from oracle import lyssa_oracle as lo
+    X = torch.from_numpy(np.ascontiguousarray(lo.synthetic_descriptors(b * 8, n, seed=0).T)).to(dev).t()
+    rng = np.random.default_rng(1)
+    D = torch.from_numpy(np.ascontiguousarray(lo.norm_cols(np.abs(rng.standard_normal((n, K)))).astype(np.float32))).to(dev)
+    A = torch.zeros((K, K), device=dev); B = torch.zeros((n, K), device=dev)
+    enc = sparse_encoder("bomp", {"n_nonzero_coefs": k}, verbose=False)
+
+    def timed(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev); e0.record(); out = fn(); e1.record(); torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1), out
+
+    st = {"encode": [], "accumulate": [], "update": []}
+    for it in range(9):
+        Xb = X[:, (it % 8) * b:(it % 8 + 1) * b]
+        t1, codes = timed(lambda: enc.encode_sparse(Xb, D))
+        t2, _ = timed(lambda: engine.odl_accumulate_(Xb, codes, 0.9, A, B))
+        t3, _ = timed(lambda: engine.odl_update_dict_(D, A, B))
+        if it > 0:
+            st["encode"].append(t1); st["accumulate"].append(t2); st["update"].append(t3)
+    med = {key: float(np.median(v)) for key, v in st.items()}
+    return sum(med.values()), med
+
+
 def sibling_coders_ms(dev, n=64, K=1024, N=1 << 20, k=5, reps=3):
     """'thresh' and 'iht'  on the headline workload's shape: ms per 1M signals, codes stay sparse."""
     import torch
@@ -402,6 +432,13 @@ def run_own(args):
         except Exception as exc:
             spm_note = "failed: %r" % (exc,)
 
+    odl_ms, odl_stages, odl_note = None, None, None
+    if not args.no_extras and rank == 0:
+        try:
+            odl_ms, odl_stages = odl_minibatch_ms(dev)
+        except Exception as exc:
+            odl_note = "failed: %r" % (exc,)
+
     sib_ms, sib_note = None, None
     if not args.no_extras and rank == 0:
         try:
@@ -457,6 +494,8 @@ def run_own(args):
                                           "note": ksvd_note},
                        "scspm_pipeline": {"workload": "128 synthetic 256x256 images (rank 0 only) -> dense SIFT 16x16 / step 6 (1681 descriptors per image) -> Batch-OMP D 128x1024 k=5 -> 3-level max-|z| pooling + l2, images resident on the device",
                                           "images_per_s": spm_rate, "note": spm_note},
+                       "odl_minibatch": {"workload": "ODL minibatch (rank 0 only): 4096 SIFT-like 128-d descriptors, D 128x2048, k=5, beta=0.9: encode -> A,B statistics -> dictionary update",
+                                         "ms_per_minibatch": odl_ms, "stages_ms": odl_stages, "note": odl_note},
                        "sibling_coders": {"workload": "'thresh' / 'iht' coders, 1M synthetic patches (rank 0 only), D 64x1024, k=5, eta=0.2, sparse codes out unless noted",
                                           "ms_per_1M_signals": sib_ms, "note": sib_note}},
         }
