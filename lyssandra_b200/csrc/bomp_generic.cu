@@ -168,11 +168,8 @@ int launch_warp_kernel(const float* alpha, const float* G, int K, int64_t C, int
 {
     size_t smem = sizeof(WarpScratch) * WARPS;
     auto kern = bomp_warp_kernel<EPL>;
-    static bool configured = false;
-    if (!configured) {
-        LYS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    // function attributes are per device and one process may drive several GPUs: set it on every launch
+    LYS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks = (C + WARPS - 1) / WARPS;
     int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;

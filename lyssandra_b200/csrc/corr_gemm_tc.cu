@@ -323,11 +323,8 @@ int corr_gemm_tc(const float* X, int64_t xfs, int64_t xss, const void* planes,
 {
     if (!corr_gemm_tc_supported(n, K)) return LYS_EUNSUPPORTED;
     if (C <= 0) return LYS_OK;
-    static bool configured = false;
-    if (!configured) {
-        LYS_CUDA(cudaFuncSetAttribute(corr_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-        configured = true;
-    }
+    // function attributes are per device and one process may drive several GPUs: set it on every launch
+    LYS_CUDA(cudaFuncSetAttribute(corr_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     const int n_slices = K / TN;
     const int64_t n_tiles = (C + TM - 1) / TM;
     int groups = sm_count() / n_slices;

@@ -286,14 +286,11 @@ int launch_select(bool use_abs, const float* alpha, float scale, const int32_t* 
         return launch_select_reg<32>(use_abs, alpha, scale, pidx, pval, pk, K, C, k, idx, val, nsel, Z, zas, zss, stream);
     }
     const size_t smem = (size_t)SEL_WARPS * K * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        LYS_CUDA(cudaFuncSetAttribute(select_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      SEL_WARPS * LYS_MAX_ATOMS * (int)sizeof(float)));
-        LYS_CUDA(cudaFuncSetAttribute(select_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      SEL_WARPS * LYS_MAX_ATOMS * (int)sizeof(float)));
-        configured = true;
-    }
+    // function attributes are per device and one process may drive several GPUs: set it on every launch
+    if (use_abs)
+        LYS_CUDA(cudaFuncSetAttribute(select_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+        LYS_CUDA(cudaFuncSetAttribute(select_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200u << 10) / std::max<size_t>(smem, 1)));
     const int64_t blocks = std::min<int64_t>((C + SEL_WARPS - 1) / SEL_WARPS, (int64_t)sm_count() * per_sm);
     if (use_abs)
