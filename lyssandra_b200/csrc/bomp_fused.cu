@@ -609,83 +609,83 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                     if (nsel) nsel[sig] = k;
                 }
             } else {
-            for (int j = 0; j < k; ++j) {
-                // ---- :322 argmax |alpha_j| over all atoms, first maximum
-                ArgmaxStateR am;
-                am.run_max = -1.f;
-                am.run_piece = 0;
+                for (int j = 0; j < k; ++j) {
+                    // ---- :322 argmax |alpha_j| over all atoms, first maximum
+                    ArgmaxStateR am;
+                    am.run_max = -1.f;
+                    am.run_piece = 0;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) am.kept[i] = 0u;
-                const uint32_t qq = (uint32_t)(r * k + j);
-                const uint32_t u0 = (qq * NS + s) * (uint32_t)nch;
+                    for (int i = 0; i < 32; ++i) am.kept[i] = 0u;
+                    const uint32_t qq = (uint32_t)(r * k + j);
+                    const uint32_t u0 = (qq * NS + s) * (uint32_t)nch;
 #pragma unroll 1
-                for (int c = 0; c < nch; ++c) {
-                    const uint32_t stg = (u0 + c) & (NSTG - 1);
-                    mbar_wait(bar_local + 8 * (8 + 8 * s + c), qq & 1);
-                    fence_after();
-                    pt.lap(2, lane);
-                    const uint32_t ta = tq + stg * CH;
-                    uint32_t b0[32], b1[32];
-                    LYS_TMEM_LD_X32(ta, b0);
+                    for (int c = 0; c < nch; ++c) {
+                        const uint32_t stg = (u0 + c) & (NSTG - 1);
+                        mbar_wait(bar_local + 8 * (8 + 8 * s + c), qq & 1);
+                        fence_after();
+                        pt.lap(2, lane);
+                        const uint32_t ta = tq + stg * CH;
+                        uint32_t b0[32], b1[32];
+                        LYS_TMEM_LD_X32(ta, b0);
 #pragma unroll
-                    for (int sc = 0; sc < NP; sc += 2) {
-                        LYS_TMEM_WAIT_X32(b0);
-                        LYS_TMEM_LD_X32(ta + (sc + 1) * 32, b1);
-                        if (!(dbg & 4)) scan_piece_r(b0, c * NP + sc, am);
-                        LYS_TMEM_WAIT_X32(b1);
-                        if (sc + 2 < NP) LYS_TMEM_LD_X32(ta + (sc + 2) * 32, b0);
-                        else {
-                            fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * (24 + 8 * s + c));
+                        for (int sc = 0; sc < NP; sc += 2) {
+                            LYS_TMEM_WAIT_X32(b0);
+                            LYS_TMEM_LD_X32(ta + (sc + 1) * 32, b1);
+                            if (!(dbg & 4)) scan_piece_r(b0, c * NP + sc, am);
+                            LYS_TMEM_WAIT_X32(b1);
+                            if (sc + 2 < NP) LYS_TMEM_LD_X32(ta + (sc + 2) * 32, b0);
+                            else {
+                                fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * (24 + 8 * s + c));
+                            }
+                            if (!(dbg & 4)) scan_piece_r(b1, c * NP + sc + 1, am); else am.kept[sc] ^= b0[sc] ^ b1[sc + 1];
                         }
-                        if (!(dbg & 4)) scan_piece_r(b1, c * NP + sc + 1, am); else am.kept[sc] ^= b0[sc] ^ b1[sc + 1];
+                        pt.lap(3, lane);
                     }
-                    pt.lap(3, lane);
-                }
-                const bool last = (j + 1 >= k);
-                const int run_idx = argmax_finish_r(am);
-                if (!st.done && !(dbg & 8)) {
-                    switch (j) {
+                    const bool last = (j + 1 >= k);
+                    const int run_idx = argmax_finish_r(am);
+                    if (!st.done && !(dbg & 8)) {
+                        switch (j) {
 #define LYS_STEP(JJ) case JJ: if constexpr (JJ < KNZ) update_step<JJ, KNZ>(st, run_idx, last, k, Dt, G, K, U, slotA, row); break;
-                        LYS_STEP(0) LYS_STEP(1) LYS_STEP(2) LYS_STEP(3) LYS_STEP(4)
-                        LYS_STEP(5) LYS_STEP(6) LYS_STEP(7) LYS_STEP(8) LYS_STEP(9)
+                            LYS_STEP(0) LYS_STEP(1) LYS_STEP(2) LYS_STEP(3) LYS_STEP(4)
+                            LYS_STEP(5) LYS_STEP(6) LYS_STEP(7) LYS_STEP(8) LYS_STEP(9)
 #undef LYS_STEP
-                        default: break;
+                            default: break;
+                        }
                     }
+                    if (!last) {
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * s);
+                    }
+                    pt.lap(4, lane);
                 }
-                if (!last) {
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * s);
+                // ---- :354 z = L^-T y, outputs
+                if (live) {
+                    float z[KNZ];
+#pragma unroll
+                    for (int rr = KNZ - 1; rr >= 0; --rr) {
+                        if (rr < st.cnt) {
+                            float sacc = st.y[rr];
+#pragma unroll
+                            for (int c = KNZ - 1; c > rr; --c) if (c < st.cnt) sacc = fmaf(-st.L[c][rr], z[c], sacc);
+                            z[rr] = sacc * st.dinv[rr];
+                        } else {
+                            z[rr] = 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int m = 0; m < KNZ; ++m) {
+                        if (m < k) {
+                            const bool has = m < st.cnt;
+                            idx[sig * k + m] = has ? st.sel[m] : -1;
+                            val[sig * k + m] = has ? z[m] : 0.f;
+                        }
+                    }
+                    if (nsel) nsel[sig] = st.cnt;
                 }
-                pt.lap(4, lane);
             }
-            // ---- :354 z = L^-T y, outputs
-            if (live) {
-                float z[KNZ];
-#pragma unroll
-                for (int rr = KNZ - 1; rr >= 0; --rr) {
-                    if (rr < st.cnt) {
-                        float sacc = st.y[rr];
-#pragma unroll
-                        for (int c = KNZ - 1; c > rr; --c) if (c < st.cnt) sacc = fmaf(-st.L[c][rr], z[c], sacc);
-                        z[rr] = sacc * st.dinv[rr];
-                    } else {
-                        z[rr] = 0.f;
-                    }
-                }
-#pragma unroll
-                for (int m = 0; m < KNZ; ++m) {
-                    if (m < k) {
-                        const bool has = m < st.cnt;
-                        idx[sig * k + m] = has ? st.sel[m] : -1;
-                        val[sig * k + m] = has ? z[m] : 0.f;
-                    }
-                }
-                if (nsel) nsel[sig] = st.cnt;
-            }
-            }   // MODE 0
             if (Z && tile < n_tiles) {                 // hand the tile to the dense-row writer of this slot
                 __syncwarp();
                 if (lane == 0) { __threadfence(); atomicAdd(tile_ready + s, 1u); }
