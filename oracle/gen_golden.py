@@ -56,11 +56,28 @@ def thresh_section(ref):
     np.savez_compressed(os.path.join(OUT, "thresh.npz"), **out)
 
 
+def ksvd_exact_section(ref):
+    """one sweep of the live reference's exact ksvd() (ksvd.py:19-43) from seeded (X, D, Z),
+    one atom unused; the global NumPy RNG (which randomized_svd draws from) is seeded with 5."""
+    X = lo.synthetic_patches(300, 64, seed=60).astype(np.float64)
+    D0 = lo.synthetic_dictionary(32, 64, seed=61).astype(np.float64)
+    Z0 = lo.sparse_encoder("bomp", {"n_nonzero_coefs": 3}, verbose=False).encode(X, D0)
+    Z0[9, :] = 0
+    np.random.seed(5)
+    with rl.quiet():
+        D1, Z1, unused = ref.ksvd(X, D0.copy(), Z0.copy(), n_cycles=1, verbose=False)
+    np.savez_compressed(os.path.join(OUT, "ksvd_exact.npz"), X=X.astype(np.float32), D0=D0, Z0=Z0, D1=D1, Z1=Z1,
+                        unused=np.array(unused, dtype=np.int32), seed=5)
+
+
 def main():
     ref = rl.load()
     os.makedirs(OUT, exist_ok=True)
     if sys.argv[1:] == ["thresh"]:
         thresh_section(ref)
+        return
+    if sys.argv[1:] == ["ksvd_exact"]:
+        ksvd_exact_section(ref)
         return
 
     # ---- (7) seeded random, BASELINE cfg1 shape cut to 512 signals: n=64, K=256, k=5
@@ -209,6 +226,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "dsift.npz"), **out)
 
     thresh_section(ref)
+    ksvd_exact_section(ref)
 
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

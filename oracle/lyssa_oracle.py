@@ -288,6 +288,35 @@ def approx_ksvd(Y, D, X, n_cycles=1, verbose=False):
     return D, X, unused
 
 
+def ksvd(Y, D, X, n_cycles=1, verbose=False, svd="randomized"):
+    """Exact K-SVD sweep, D and X mutated IN PLACE — lyssa/dict_learning/ksvd.py:19-43 (SURVEY.md section 8f
+    row 4; no device path yet, this is the checker it will be built against).  Per atom: users = X[k]!=0 (:31),
+    unused atoms recorded and skipped (:32-34), Rk = R[:,users] + d x (:36), (d, x) <- top singular triplet of Rk
+    (:37-39), R[:,users] = Rk - d x (:41).  The reference takes the triplet from scikit-learn's
+    ``randomized_svd(Rk, n_components=1, n_iter=10, flip_sign=False)`` (a third-party dependency, not pinned by the
+    reference; 1.9.0 in this image) with the global NumPy RNG: the common sign of (d, x) is arbitrary, d x^T is not.
+    ``svd="lapack"`` takes it from np.linalg.svd instead (deterministic; same d x^T wherever sigma_1 > sigma_2)."""
+    n_atoms = D.shape[1]
+    unused = []
+    R = Y - np.dot(D, X)
+    for _ in range(n_cycles):
+        for k in range(n_atoms):
+            users = X[k, :] != 0
+            if not np.any(users):
+                unused.append(k)
+                continue
+            Rk = R[:, users] + np.outer(D[:, k], X[k, users])
+            if svd == "randomized":
+                from sklearn.utils.extmath import randomized_svd
+                U, S, V = randomized_svd(Rk, n_components=1, n_iter=10, flip_sign=False)          # :37
+            else:
+                U, S, V = np.linalg.svd(Rk, full_matrices=False)
+            D[:, k] = U[:, 0]
+            X[k, users] = V[0, :] * S[0]
+            R[:, users] = Rk - np.outer(D[:, k], X[k, users])
+    return D, X, unused
+
+
 def ksvd_dict_learn(X, n_atoms, init_dict="data", sparse_coder=None, max_iter=20, non_neg=False,
                     approx=False, eta=None, n_cycles=1, n_jobs=1, mmap=False, verbose=True,
                     history=None):

@@ -108,7 +108,7 @@ def load():
 
     Attributes: fast_dot, norm, normalize, norm_cols, frobenius_squared, run_parallel,
     gen_batches, gen_even_batches, batch_omp, omp, sparse_encoder, approx_error,
-    init_dictionary, average_mutual_coherence, approx_ksvd, ksvd_dict_learn, ksvd_coder,
+    init_dictionary, average_mutual_coherence, approx_ksvd, ksvd, ksvd_dict_learn, ksvd_coder,
     online_dict_learn, online_dictionary_coder, projected_grad_desc, dictionary_learner.
     """
     global _cache
@@ -178,6 +178,11 @@ def load():
     for name in ("approx_error", "force_mi", "average_mutual_coherence", "init_dictionary"):
         ks_ns[name] = du_ns[name]
     ks_ns["set_openblas_threads"] = utils_ns["set_openblas_threads"]
+    try:    # exact ksvd() (ksvd.py:19-43) calls scikit-learn's randomized_svd (ksvd.py:7,:37), a third-party dependency
+        from sklearn.utils.extmath import randomized_svd as _rsvd
+        ks_ns["randomized_svd"] = _rsvd
+    except Exception:                                                    # ksvd() then raises NameError when called
+        pass
     _load_defs("lyssa/dict_learning/ksvd.py", ks_ns)
     # ksvd_dict_learn does `from .utils import init_dictionary` inside the function (ksvd.py:152);
     # give the function's globals a package context that resolves it.
@@ -240,6 +245,7 @@ def load():
     ref.init_dictionary = du_ns["init_dictionary"]
     ref.average_mutual_coherence = du_ns["average_mutual_coherence"]
     ref.approx_ksvd = ks_ns["approx_ksvd"]
+    ref.ksvd = ks_ns["ksvd"]
     ref.ksvd_dict_learn = ks_ns["ksvd_dict_learn"]
     ref.ksvd_coder = ks_ns["ksvd_coder"]
     ref.online_dict_learn = od_ns["online_dict_learn"]
