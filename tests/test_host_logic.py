@@ -118,3 +118,32 @@ def test_world_size_2_gloo_sharding_and_suffstat_allreduce():
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_gloo_worker, args=(2, port, 1001, out), nprocs=2, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+def test_product_code_never_touches_the_oracle_or_the_reference_tree():
+    """the oracle is test infrastructure: nothing under lyssandra_b200/ or lyssa/ may import it, name the reference
+    tree, or carry a CPU fallback for a coder (the C-ABI is the only compute path)"""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bad = []
+    for pkg in ("lyssandra_b200", "lyssa"):
+        for dirpath, _, files in os.walk(os.path.join(root, pkg)):
+            for f in files:
+                if not f.endswith((".py", ".cu", ".cuh", ".h")):
+                    continue
+                text = open(os.path.join(dirpath, f), encoding="utf-8", errors="replace").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M) or "lyssa_oracle" in text:
+                    bad.append((f, "imports the oracle"))
+                if re.search(r"open\(.*/root/reference|sys\.path.*reference", text):
+                    bad.append((f, "reads the reference tree"))
+    assert not bad, bad
+
+
+def test_thresholding_coders_without_gpu_fail_loudly():
+    from lyssandra_b200 import engine
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    for alg, params in (("thresh", {"n_nonzero_coefs": 2}), ("iht", {"n_nonzero_coefs": 2, "eta": 0.1, "n_iter": 1})):
+        with pytest.raises(RuntimeError):
+            sparse_encoder(alg, params, verbose=False).encode(np.zeros((4, 3), dtype=np.float32), np.eye(4, dtype=np.float32))
