@@ -170,9 +170,12 @@ LYS_API int lys_build_atom_csr(const int32_t* idx, const float* val, int64_t N, 
  * updated IN PLACE as in the reference; R (N,n) is the residual from lys_residual and is
  * kept current.  unused (K) int32 receives 1 for atoms without users (:112-115).
  * `comm` is NULL for one GPU, or a handle from lys_comm_create when the signals are
- * sharded over ranks: the per-atom (n+2)-float partial sums are then all-reduced inside the
- * kernel through peer-mapped buffers (see below). */
-LYS_API size_t lys_ksvd_sweep_workspace_bytes(int n, int K);
+ * sharded over ranks: the per-atom sums (2n+3 fixed-point words: the look-ahead form of
+ * R_k x, x.x and the user count) are then all-reduced inside the kernel through peer-mapped
+ * mailboxes (see below).  The reduction is integer arithmetic, so the sweep is bitwise
+ * reproducible and every rank ends with bit-identical D.  `idx` is the code index array the
+ * CSR was built from (N,k). */
+LYS_API size_t lys_ksvd_sweep_workspace_bytes(int n, int K, int64_t N, int k);
 LYS_API int lys_approx_ksvd_sweep(float* R, float* D, int64_t ldd,
                           const int32_t* idx, float* val,
                           const int32_t* rowptr, const int32_t* entries,

@@ -15,7 +15,7 @@ CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "liblyssa_b200.so")
 _STAMP = os.path.join(_PKG, "csrc", ".build_stamp")
 
-SOURCES = ["runtime.cu", "gemm.cu", "bomp_generic.cu", "bomp_fast.cu", "corr_gemm_tc.cu", "bomp_fused.cu", "bomp_tc3.cu", "bomp.cu", "ksvd.cu", "ksvd_sweep.cu", "odl.cu", "comm.cu", "spm.cu", "dsift.cu", "thresh.cu"]
+SOURCES = ["runtime.cu", "gemm.cu", "bomp_generic.cu", "bomp_fast.cu", "corr_gemm_tc.cu", "bomp_fused.cu", "bomp.cu", "ksvd.cu", "ksvd_sweep.cu", "odl.cu", "comm.cu", "spm.cu", "dsift.cu", "thresh.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--threads", "0"]
 
@@ -39,19 +39,30 @@ def _fingerprint():
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, bringup: bool = False) -> str:
+    """Product library, or with ``bringup`` a separate liblyssa_b200_bringup.so compiled with -DLYS_BRINGUP
+    (in-kernel phase timers and their debug hooks; load it through LYSSA_B200_LIB — scripts only)."""
+    if bringup:
+        return _build_to(os.path.join(_PKG, "liblyssa_b200_bringup.so"), os.path.join(_PKG, "build_bringup"),
+                         ["-DLYS_BRINGUP"], verbose)
     fp = _fingerprint()
     if not force and os.path.isfile(LIB_PATH) and os.path.isfile(_STAMP):
         with open(_STAMP) as fh:
             if fh.read().strip() == fp:
                 return LIB_PATH
+    _build_to(LIB_PATH, os.path.join(_PKG, "build"), [], verbose)
+    with open(_STAMP, "w") as fh:
+        fh.write(fp)
+    return LIB_PATH
+
+
+def _build_to(lib_path, objdir, extra_flags, verbose):
     nvcc = _nvcc()
-    objdir = os.path.join(_PKG, "build")
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + extra_flags + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -63,14 +74,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose and out:
             sys.stderr.write(out)
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcuda"]
+    cmd = [nvcc, "-shared", "-o", lib_path] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcuda"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n%s" % res.stdout)
-    with open(_STAMP, "w") as fh:
-        fh.write(fp)
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, bringup="--bringup" in sys.argv))

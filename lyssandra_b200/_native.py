@@ -41,7 +41,7 @@ SIGNATURES = {
                              c_vp, c_vp, c_vp, c_sz, c_vp]),
     "lys_atom_csr_workspace_bytes": (c_sz, [c_int, c_i64, c_int]),
     "lys_build_atom_csr": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
-    "lys_ksvd_sweep_workspace_bytes": (c_sz, [c_int, c_int]),
+    "lys_ksvd_sweep_workspace_bytes": (c_sz, [c_int, c_int, c_i64, c_int]),
     "lys_approx_ksvd_sweep": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int,
                                       c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "lys_norm_cols": (c_int, [c_vp, c_i64, c_int, c_int, c_vp]),
@@ -85,9 +85,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = os.environ.get("LYSSA_B200_LIB") or _build.LIB_PATH          # override: debugging builds only
-    if not os.path.isfile(path) or os.environ.get("LYSSA_B200_REBUILD"):
-        path = _build.build()
+    path = os.environ.get("LYSSA_B200_LIB")                              # override: bring-up builds only
+    if not path:
+        # build() compares the source fingerprint with the stamp of the in-tree .so and returns at once when they
+        # agree, so a stale library (sources edited after the last build) is never loaded silently
+        path = _build.build(force=bool(os.environ.get("LYSSA_B200_REBUILD")))
     lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)           # AttributeError if the library lacks a declared symbol

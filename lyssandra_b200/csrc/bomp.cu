@@ -65,14 +65,12 @@ constexpr int NF_MAX_HOOK = 128;
 // signals per correlation chunk: the (chunk x K) fp32 Alpha tile is written by the GEMM kernel
 // and read once by the greedy kernel.  Measured on B200 (profiles/README.md): per-launch fixed
 // costs (D-plane staging, tail waves) outweigh L2 residency of the tile — 16/64/128/512 MB
-// chunks give 10.8/6.9/6.2/5.5 ms per 1M-patch encode — so the default is 512 MB
-// (LYS_CHUNK_MB overrides for experiments).
+// chunks give 10.8/6.9/6.2/5.5 ms per 1M-patch encode — so the chunk is 512 MB.
 constexpr int64_t kChunkBytesTarget = 512ll << 20;
 
 int64_t generic_chunk(int K, int64_t N)
 {
-    int64_t target = kChunkBytesTarget;
-    if (const char* e = getenv("LYS_CHUNK_MB")) { long v = atol(e); if (v >= 1 && v <= 4096) target = (int64_t)v << 20; }
+    const int64_t target = kChunkBytesTarget;
     int64_t c = target / ((int64_t)K * 4);
     c = std::max<int64_t>(1024, c / 1024 * 1024);
     return std::min<int64_t>(c, std::max<int64_t>(N, 1));
@@ -147,9 +145,8 @@ extern "C" int lys_bomp_encode(const float* X, int64_t xfs, int64_t xss,
     float* alpha = reinterpret_cast<float*>(workspace);
     const int64_t chunk = generic_chunk(K, N);
     void* planes = reinterpret_cast<unsigned char*>(workspace) + align_up((size_t)chunk * (size_t)K * sizeof(float), 256);
-    const char* gemm_env = getenv("LYS_GEMM");
-    const bool use_tc = corr_gemm_tc_supported(n, K) && !(gemm_env && !strcmp(gemm_env, "simt"));
-    const bool fast = bomp_fast_supported(K, k, zas, Z != nullptr, Z, zss) && !getenv("LYS_FORCE_GENERIC");
+    const bool use_tc = corr_gemm_tc_supported(n, K);
+    const bool fast = bomp_fast_supported(K, k, zas, Z != nullptr, Z, zss);
     if (use_tc) {
         rc = corr_gemm_tc_prepare(D, ldd, n, K, planes, stream);
         if (rc) return rc;
@@ -246,34 +243,53 @@ extern "C" int lys_codes_to_dense(const int32_t* idx, const float* val, int64_t 
 // --------------------------------------------------------------------------- host pipeline
 namespace {
 
+// One pipeline per device: staging buffers, two copy/compute streams and the "dictionary ready" event are created
+// once and reused.  Each pipeline has its own lock, so sparse_encoder(n_jobs=G).encode(numpy) — one host thread per
+// GPU (lyssa/utils/__init__.py:92-146 forks one worker per job) — drives G devices concurrently; two callers that
+// target the SAME device take turns.
 struct HostPipe {
-    int device = -1;
+    std::mutex mu;
+    bool ready = false;
     size_t bytes = 0;
     unsigned char* base = nullptr;
     cudaStream_t streams[2] = {nullptr, nullptr};
+    cudaEvent_t dict_ready = nullptr;
 };
-std::mutex g_pipe_mu;
-std::vector<HostPipe> g_pipes;
+constexpr int kMaxDevices = 64;
+HostPipe g_pipes[kMaxDevices];
 
-HostPipe* get_pipe(int device, size_t bytes)
+// caller holds p.mu and has made `device` current
+int pipe_reserve(HostPipe& p, size_t bytes)
 {
-    for (auto& p : g_pipes)
-        if (p.device == device) {
-            if (p.bytes < bytes) {
-                cudaFree(p.base); p.base = nullptr; p.bytes = 0;
-                if (cudaMalloc(&p.base, bytes) != cudaSuccess) return nullptr;
-                p.bytes = bytes;
-            }
-            return &p;
-        }
-    HostPipe p; p.device = device;
-    if (cudaMalloc(&p.base, bytes) != cudaSuccess) return nullptr;
-    p.bytes = bytes;
-    for (int s = 0; s < 2; ++s)
-        if (cudaStreamCreateWithFlags(&p.streams[s], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    g_pipes.push_back(p);
-    return &g_pipes.back();
+    if (!p.ready) {
+        for (int s = 0; s < 2; ++s) LYS_CUDA(cudaStreamCreateWithFlags(&p.streams[s], cudaStreamNonBlocking));
+        LYS_CUDA(cudaEventCreateWithFlags(&p.dict_ready, cudaEventDisableTiming));
+        p.ready = true;
+    }
+    if (p.bytes < bytes) {
+        if (p.base) { LYS_CUDA(cudaFree(p.base)); p.base = nullptr; p.bytes = 0; }
+        LYS_CUDA(cudaMalloc(&p.base, bytes));
+        p.bytes = bytes;
+    }
+    return LYS_OK;
 }
+
+// on any failure inside the chunk loop: no async copy may still be writing into the caller's buffers when we return
+int pipe_fail(HostPipe& p, int rc)
+{
+    cudaStreamSynchronize(p.streams[0]);
+    cudaStreamSynchronize(p.streams[1]);
+    return rc;
+}
+
+#define LYS_PIPE_CUDA(pipe, call)                                                            \
+    do {                                                                                     \
+        cudaError_t _e = (call);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            ::lys::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return pipe_fail(pipe, LYS_ECUDA);                                               \
+        }                                                                                    \
+    } while (0)
 
 }  // namespace
 
@@ -292,9 +308,11 @@ extern "C" int lys_bomp_encode_host(const float* X, int64_t xfs, int64_t xss,
     LYS_CHECK_ARG(!Z || (zas == 1 && zss >= K) || (zss == 1 && zas >= N),
                   "lys_bomp_encode_host: Z must be signal-major (atom stride 1) or atom-major (signal stride 1)");
     if (N == 0) return LYS_OK;
-    std::lock_guard<std::mutex> lock(g_pipe_mu);
     if (device >= 0) LYS_CUDA(cudaSetDevice(device));
     else LYS_CUDA(cudaGetDevice(&device));
+    LYS_CHECK_ARG(device < kMaxDevices, "lys_bomp_encode_host: device %d out of range", device);
+    HostPipe& pipe = g_pipes[device];
+    std::lock_guard<std::mutex> lock(pipe.mu);
 
     const int64_t chunk = std::min<int64_t>(N, 32768);
     const size_t ws_bytes = align_up(lys_bomp_workspace_bytes(n, K, chunk, k), 256);
@@ -304,10 +322,10 @@ extern "C" int lys_bomp_encode_host(const float* X, int64_t xfs, int64_t xss,
     const size_t s_bytes = align_up((size_t)chunk * 4, 256);
     const size_t z_bytes = Z ? align_up((size_t)chunk * K * 4, 256) : 0;
     const size_t slot_bytes = x_bytes + 2 * i_bytes + s_bytes + z_bytes + ws_bytes;
-    HostPipe* pipe = get_pipe(device, d_bytes + g_bytes + 2 * slot_bytes);
-    if (!pipe) { set_error("lys_bomp_encode_host: device allocation failed"); return LYS_ECUDA; }
+    int rc = pipe_reserve(pipe, d_bytes + g_bytes + 2 * slot_bytes);
+    if (rc) return rc;
 
-    unsigned char* p = pipe->base;
+    unsigned char* p = pipe.base;
     float* dD = reinterpret_cast<float*>(p); p += d_bytes;
     float* dG = reinterpret_cast<float*>(p); p += g_bytes;
     struct Slot { float* x; int32_t* idx; float* val; int32_t* nsel; float* z; void* ws; } slot[2];
@@ -319,50 +337,47 @@ extern "C" int lys_bomp_encode_host(const float* X, int64_t xfs, int64_t xss,
         slot[s].z = Z ? reinterpret_cast<float*>(p) : nullptr; p += z_bytes;
         slot[s].ws = p; p += ws_bytes;
     }
-    cudaStream_t s0 = pipe->streams[0], s1 = pipe->streams[1];
-    LYS_CUDA(cudaMemcpy2DAsync(dD, (size_t)K * 4, D, (size_t)ldd * 4, (size_t)K * 4, n, cudaMemcpyHostToDevice, s0));
-    int rc = lys_gram(dD, K, n, K, dG, s0);
-    if (rc) return rc;
-    cudaEvent_t ready;
-    LYS_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-    LYS_CUDA(cudaEventRecord(ready, s0));
-    LYS_CUDA(cudaStreamWaitEvent(s1, ready, 0));
+    cudaStream_t s0 = pipe.streams[0], s1 = pipe.streams[1];
+    LYS_PIPE_CUDA(pipe, cudaMemcpy2DAsync(dD, (size_t)K * 4, D, (size_t)ldd * 4, (size_t)K * 4, n, cudaMemcpyHostToDevice, s0));
+    rc = lys_gram(dD, K, n, K, dG, s0);
+    if (rc) return pipe_fail(pipe, rc);
+    LYS_PIPE_CUDA(pipe, cudaEventRecord(pipe.dict_ready, s0));
+    LYS_PIPE_CUDA(pipe, cudaStreamWaitEvent(s1, pipe.dict_ready, 0));
 
     const bool x_sig_major = (xfs == 1);
     const bool z_sig_major = (zas == 1);
     int which = 0;
     for (int64_t c0 = 0; c0 < N; c0 += chunk, which ^= 1) {
         const int64_t C = std::min(chunk, N - c0);
-        cudaStream_t st = pipe->streams[which];
+        cudaStream_t st = pipe.streams[which];
         Slot& sl = slot[which];
         int64_t dxfs, dxss;
         if (x_sig_major) {       // host rows of n floats, row stride xss -> device (C, n)
-            LYS_CUDA(cudaMemcpy2DAsync(sl.x, (size_t)n * 4, X + c0 * xss, (size_t)xss * 4, (size_t)n * 4, C,
-                                       cudaMemcpyHostToDevice, st));
+            LYS_PIPE_CUDA(pipe, cudaMemcpy2DAsync(sl.x, (size_t)n * 4, X + c0 * xss, (size_t)xss * 4, (size_t)n * 4, C,
+                                                  cudaMemcpyHostToDevice, st));
             dxfs = 1; dxss = n;
         } else {                 // host (n, N) feature-major -> device (n, C)
-            LYS_CUDA(cudaMemcpy2DAsync(sl.x, (size_t)C * 4, X + c0, (size_t)xfs * 4, (size_t)C * 4, n,
-                                       cudaMemcpyHostToDevice, st));
+            LYS_PIPE_CUDA(pipe, cudaMemcpy2DAsync(sl.x, (size_t)C * 4, X + c0, (size_t)xfs * 4, (size_t)C * 4, n,
+                                                  cudaMemcpyHostToDevice, st));
             dxfs = C; dxss = 1;
         }
         int64_t dzas = z_sig_major ? 1 : C, dzss = z_sig_major ? K : 1;
         rc = lys_bomp_encode(sl.x, dxfs, dxss, dD, K, dG, n, K, C, k, sl.idx, sl.val, sl.nsel,
                              sl.z, dzas, dzss, sl.ws, ws_bytes, st);
-        if (rc) return rc;
-        if (idx) LYS_CUDA(cudaMemcpyAsync(idx + c0 * k, sl.idx, (size_t)C * k * 4, cudaMemcpyDeviceToHost, st));
-        if (val) LYS_CUDA(cudaMemcpyAsync(val + c0 * k, sl.val, (size_t)C * k * 4, cudaMemcpyDeviceToHost, st));
-        if (nsel) LYS_CUDA(cudaMemcpyAsync(nsel + c0, sl.nsel, (size_t)C * 4, cudaMemcpyDeviceToHost, st));
+        if (rc) return pipe_fail(pipe, rc);
+        if (idx) LYS_PIPE_CUDA(pipe, cudaMemcpyAsync(idx + c0 * k, sl.idx, (size_t)C * k * 4, cudaMemcpyDeviceToHost, st));
+        if (val) LYS_PIPE_CUDA(pipe, cudaMemcpyAsync(val + c0 * k, sl.val, (size_t)C * k * 4, cudaMemcpyDeviceToHost, st));
+        if (nsel) LYS_PIPE_CUDA(pipe, cudaMemcpyAsync(nsel + c0, sl.nsel, (size_t)C * 4, cudaMemcpyDeviceToHost, st));
         if (Z) {
             if (z_sig_major)
-                LYS_CUDA(cudaMemcpy2DAsync(Z + c0 * zss, (size_t)zss * 4, sl.z, (size_t)K * 4, (size_t)K * 4, C,
-                                           cudaMemcpyDeviceToHost, st));
+                LYS_PIPE_CUDA(pipe, cudaMemcpy2DAsync(Z + c0 * zss, (size_t)zss * 4, sl.z, (size_t)K * 4, (size_t)K * 4, C,
+                                                      cudaMemcpyDeviceToHost, st));
             else
-                LYS_CUDA(cudaMemcpy2DAsync(Z + c0, (size_t)zas * 4, sl.z, (size_t)C * 4, (size_t)C * 4, K,
-                                           cudaMemcpyDeviceToHost, st));
+                LYS_PIPE_CUDA(pipe, cudaMemcpy2DAsync(Z + c0, (size_t)zas * 4, sl.z, (size_t)C * 4, (size_t)C * 4, K,
+                                                      cudaMemcpyDeviceToHost, st));
         }
     }
-    LYS_CUDA(cudaStreamSynchronize(s0));
-    LYS_CUDA(cudaStreamSynchronize(s1));
-    cudaEventDestroy(ready);
+    LYS_PIPE_CUDA(pipe, cudaStreamSynchronize(s0));
+    LYS_PIPE_CUDA(pipe, cudaStreamSynchronize(s1));
     return LYS_OK;
 }

@@ -14,9 +14,19 @@
 //              L <- [L; w, sqrt(pivot)]               (:337,:348-349)
 //              z = L^-T L^-1 alpha0[I]                (:353-354; alpha0[I] = D_I^T x in fp32)
 //              r_{j+1} = x - D_I z
-// Precision: every fp32 operand is scaled by a power of two and split exactly into two fp16
-// planes (hi = rn16(v), lo = rn16(v - hi), 22+ mantissa bits); hi*hi + lo*hi + hi*lo are
-// accumulated in fp32 in TMEM (3 MMAs per k-step; the dropped lo*lo term is 2^-22 relative).
+// Precision, default ("screen") mode: the tensor cores only RANK.  Every operand is scaled by a power of two and
+// rounded to fp16 (hi = rn16(v)); ONE product hi*hi per k-step is accumulated in fp32 in TMEM.  Its distance to the
+// exact correlation is bounded, per signal and step, by  E = ||r - r~|| max_c||d~_c|| + ||r|| max_c||d_c - d~_c||
+// (+ the accumulation error), all four norms measured, none assumed.  The scan keeps the maximum M, the best value
+// outside the winning 32-column piece and the piece maxima; if nothing else comes within 2E of M the winner is
+// the exact argmax (certified: ~97 % of the decisions at cfg2).  Otherwise the warp recomputes, cooperatively and in
+// fp32 from the atom-major fp32 dictionary, every column of every piece whose maximum is within 2E of M and takes the
+// first maximum of those exact values: the selection is exact in all cases, the tensor work is a third of the
+// split-product scheme.  Everything after the argmax (Cholesky row, coefficients, residual) is fp32 from the fp32
+// dictionary in both modes, so the two modes return identical codes.
+// "split3" mode (LYS_BOMP_SPLIT3, kept for A/B checks and used by the 'thresh' coder, which needs k ranked values):
+// operands split exactly into two fp16 planes (hi = rn16(v), lo = rn16(v - hi), 22+ mantissa bits);
+// hi*hi + lo*hi + hi*lo accumulated in fp32 in TMEM (3 MMAs per k-step; the dropped lo*lo term is 2^-22 relative).
 //
 // Decomposition: a tile is 128 signals (TMEM lanes = MMA M); atoms are processed in chunks of
 // 256 (MMA N = one 256-column accumulator stage; two stages).  The fp16 planes of the whole
@@ -36,8 +46,8 @@
 // it waits on (the two slots alternate on the two stages; a parity wait must never be two
 // phases behind).
 //
-// Roofline: tensor pipe.  Per signal k * 2*64*K*3 fp16 flop (1.97 MFLOP at K=1024, k=5) and
-// 4n + 4K bytes of HBM traffic (x in, dense Z row out).
+// Roofline: HBM, 4n + 4K bytes per signal (x in, dense Z row out); tensor work per signal k * 2*64*K fp16 flop
+// (0.66 MFLOP at K=1024, k=5; three times that in split3 mode).
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include <cuda_fp16.h>
@@ -48,9 +58,6 @@
 namespace lys {
 
 bool profile_begin(cudaStream_t st, const char* name, cudaEvent_t* stop_out);
-int bomp_encode_tc3(const float* X, int64_t xfs, int64_t xss, const float* D, int64_t ldd, const float* G,
-                    int n, int K, int64_t N, int k, int32_t* idx, float* val, int32_t* nsel,
-                    float* Z, int64_t zss, void* planes_ws, float* Dt, float* scratch, cudaStream_t stream);
 
 namespace {
 
@@ -70,7 +77,11 @@ constexpr int A_PLANE = TM * NF * 2;     // 16 KB: one fp16 plane of a residual 
 constexpr int A_SLOT = 2 * A_PLANE;      // hi + lo
 constexpr int SMEM_BAR = 384;
 constexpr int MAX_SLOTS = 3;
-constexpr float kDictScale = 32.f;       // atoms (unit norm) are stored as 32*d: fp16 lo plane stays normal
+constexpr int PM_SLOT = 32 * TM * 4;     // screen mode: maxima of the (<= 32) 32-column pieces of every signal of a tile
+constexpr int RBUF = 8 * NF * 4;         // screen mode: one residual per signal warp, for the cooperative exact recompute
+constexpr float kAccGamma = 1.52587890625e-05f;   // 2^-16: bound on the relative error of the 64-term fp32 accumulation in TMEM
+// dictionary statistics written by dict_stats_kernel: [0] power-of-two scale s (max |s d| in [16,32)),
+// [1] max_c ||s d_c - rn16(s d_c)||, [2] max_c ||rn16(s d_c)||
 
 template <int PAIR> struct Geo {
     static constexpr int ROWS_B = CH / PAIR;            // atoms of one chunk held by one CTA
@@ -133,12 +144,19 @@ __device__ __forceinline__ float piece_absmax(const uint32_t (&r)[32])
 // half-rate ALU pipe: FMNMX3 2.0, FMUL 0.5-1.0 cycles per warp instruction, scripts/ubench/pipes.cu)
 struct ArgmaxStateR {
     float run_max;
+    float p2;                 // screen mode: largest piece maximum that is not run_max (best value outside the kept piece)
     int run_piece;
     uint32_t kept[32];
 };
-__device__ __forceinline__ void scan_piece_r(const uint32_t (&r)[32], int piece, ArgmaxStateR& am)
+// SCREEN: also records the piece maximum (pmcol[piece * TM]) and the runner-up among the piece maxima
+template <bool SCREEN>
+__device__ __forceinline__ void scan_piece_r(const uint32_t (&r)[32], int piece, ArgmaxStateR& am, float* pmcol)
 {
     const float m = piece_absmax(r);
+    if constexpr (SCREEN) {
+        pmcol[piece * TM] = m;
+        am.p2 = fmaxf(am.p2, fminf(m, am.run_max));
+    }
     if (m > am.run_max) {
         am.run_max = m;
         am.run_piece = piece;
@@ -146,13 +164,22 @@ __device__ __forceinline__ void scan_piece_r(const uint32_t (&r)[32], int piece,
         for (int i = 0; i < 32; ++i) am.kept[i] = __float_as_uint(2.0f * __uint_as_float(r[i]));
     }
 }
-__device__ __forceinline__ int argmax_finish_r(const ArgmaxStateR& am)
+// first column of the kept piece that attains the maximum; SCREEN: *s2 = largest |value| of the piece's OTHER columns
+template <bool SCREEN>
+__device__ __forceinline__ int argmax_finish_r(const ArgmaxStateR& am, float* s2)
 {
     float key[32];
     const float m2 = 2.0f * am.run_max;
 #pragma unroll
     for (int i = 0; i < 32; ++i) key[i] = fmaf(fabsf(__uint_as_float(am.kept[i])) - m2, -1.0e30f, (float)i);
-    return am.run_piece * 32 + (int)Tree3<32>::vmin(key);
+    const float first = Tree3<32>::vmin(key);
+    if constexpr (SCREEN) {
+        float o[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = (first == (float)i) ? 0.f : fabsf(__uint_as_float(am.kept[i]));
+        *s2 = 0.5f * Tree3<32>::vmax(o);
+    }
+    return am.run_piece * 32 + (int)first;
 }
 
 #ifndef LYS_ZGROUPS
@@ -167,8 +194,11 @@ __device__ __forceinline__ int argmax_finish_r(const ArgmaxStateR& am)
 
 // scale r by a power of two so that max|r| lands in [16,32), split into fp16 hi/lo planes and
 // store row `row` of the slot's A operand (canonical K-major no-swizzle layout: 16-byte chunk
-// kc of row r at kc*(TM*16) + r*16)
-__device__ __forceinline__ void store_planes(unsigned char* slotA, int row, const float (&r)[NF])
+// kc of row r at kc*(TM*16) + r*16).  SCREEN: only the hi plane exists; returns the bound E on
+// |tensor-core value - exact correlation| of this residual against any atom, in the accumulator's units
+// (both operands scaled): ||rs - rn16(rs)|| max||d~|| + ||rs|| (max||d - d~|| + gamma max||d~||), slightly inflated.
+template <bool SCREEN>
+__device__ __forceinline__ float store_planes(unsigned char* slotA, int row, const float (&r)[NF], float d_err, float d_max)
 {
     float t[22];
 #pragma unroll
@@ -180,6 +210,7 @@ __device__ __forceinline__ void store_planes(unsigned char* slotA, int row, cons
     int es = 258 - (int)(__float_as_uint(amax) >> 23);
     es = min(max(es, 1), 254);
     const float s = __uint_as_float((uint32_t)es << 23);
+    float rho2 = 0.f, drho2 = 0.f;
 #pragma unroll
     for (int kc = 0; kc < NF / 8; ++kc) {
         uint32_t hi[4], lo[4];
@@ -188,13 +219,24 @@ __device__ __forceinline__ void store_planes(unsigned char* slotA, int row, cons
             const float a = r[kc * 8 + 2 * e] * s, b = r[kc * 8 + 2 * e + 1] * s;
             const __half2 h = __floats2half2_rn(a, b);
             const float2 hf = __half22float2(h);
-            const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+            const float da = a - hf.x, db = b - hf.y;
             hi[e] = *reinterpret_cast<const uint32_t*>(&h);
-            lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+            if constexpr (SCREEN) {
+                rho2 = fmaf(a, a, fmaf(b, b, rho2));
+                drho2 = fmaf(da, da, fmaf(db, db, drho2));
+            } else {
+                const __half2 l = __floats2half2_rn(da, db);
+                lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+            }
         }
         *reinterpret_cast<uint4*>(slotA + kc * (TM * 16) + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(slotA + A_PLANE + kc * (TM * 16) + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        if constexpr (!SCREEN)
+            *reinterpret_cast<uint4*>(slotA + A_PLANE + kc * (TM * 16) + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
+    if constexpr (SCREEN)
+        return 1.001f * fmaf(sqrtf(drho2), d_max, sqrtf(rho2) * fmaf(kAccGamma, d_max, d_err));
+    else
+        return 0.f;
 }
 
 // 'thresh' mode (lyssa/sparse_coding.py:416-425): running top-KNZ of the SIGNED correlations of one signal,
@@ -241,6 +283,7 @@ template <int KNZ> struct SigState {
     int sel[KNZ];
     int cnt;
     bool done;
+    float E;                    // screen mode: error bound of the tensor-core correlations of the CURRENT residual
 };
 
 // everything that follows the argmax of step J for one signal (:323-359).
@@ -249,10 +292,10 @@ template <int KNZ> struct SigState {
 //     y_j = (L^-1 alpha0[I])_j = (d_pick . r_j) / L[j][j]        r_{j+1} = r_j - y_j u_j
 // so a step needs ONE scattered atom gather (d_pick); u_0..u_{k-3} live in a per-CTA scratch
 // laid out [vector][feature][signal] so that a warp's accesses to them are coalesced.
-template <int J, int KNZ>
+template <int J, int KNZ, bool SCREEN>
 __device__ __forceinline__ void update_step(SigState<KNZ>& st, int pick, bool last, int k,
                                             const float* __restrict__ Dt, const float* __restrict__ G, int K,
-                                            float* U, unsigned char* slotA, int row)
+                                            float* U, unsigned char* slotA, int row, float d_err, float d_max)
 {
     bool dup = false;
 #pragma unroll
@@ -311,7 +354,45 @@ __device__ __forceinline__ void update_step(SigState<KNZ>& st, int pick, bool la
         if (keep) __stcg(U + ((size_t)J * NF + f) * TM, u);
         st.r[f] = fmaf(-yj, u, st.r[f]);
     }
-    store_planes(slotA, row, st.r);
+    st.E = store_planes<SCREEN>(slotA, row, st.r, d_err, d_max);
+}
+
+// The exact first-maximum argmax for the signal of lane `src` when the tensor-core scan could not certify its
+// winner: every lane recomputes, in fp32 from the atom-major fp32 dictionary, one column of every 32-column piece
+// whose (screened) maximum lies within 2E of the best screened value — all other columns are provably smaller.
+// `thr` = M - 2E and `prow` = the signal's row of piece maxima are lane src's; rbuf is this warp's 64-float scratch.
+__device__ __forceinline__ int resolve_exact(const float (&r)[NF], int src, float thr, const float* prow, int n_pieces,
+                                             const float* __restrict__ Dt, int K, float* rbuf, int lane)
+{
+    if (lane == src) {
+#pragma unroll
+        for (int q = 0; q < NF / 4; ++q) reinterpret_cast<float4*>(rbuf)[q] = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+    }
+    const float thr_s = __shfl_sync(0xffffffffu, thr, src);
+    const float* prow_s = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, reinterpret_cast<uintptr_t>(prow), src));
+    const float pmv = (lane < n_pieces) ? prow_s[lane * TM] : -1.f;
+    unsigned cand = __ballot_sync(0xffffffffu, pmv >= thr_s);
+    float best = -1.f;
+    int bcol = 0x7fffffff;
+    while (cand) {
+        const int p = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const int col = p * 32 + lane;
+        const float4* dp = reinterpret_cast<const float4*>(Dt + (size_t)col * NF);
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll
+        for (int q = 0; q < NF / 4; ++q) {
+            const float4 d4 = __ldg(dp + q);
+            const float4 r4 = reinterpret_cast<const float4*>(rbuf)[q];
+            p0 = fmaf(d4.x, r4.x, p0); p1 = fmaf(d4.y, r4.y, p1); p2 = fmaf(d4.z, r4.z, p2); p3 = fmaf(d4.w, r4.w, p3);
+        }
+        const float v = fabsf((p0 + p1) + (p2 + p3));
+        if (v > best) { best = v; bcol = col; }                  // pieces ascend: the first maximum of this lane's columns
+    }
+    const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(best, 0.f)));
+    const unsigned pick = __reduce_min_sync(0xffffffffu, (best >= 0.f && __float_as_uint(best) == mb) ? (unsigned)bcol : 0x7fffffffu);
+    __syncwarp();                                                 // rbuf is rewritten by the next unresolved lane
+    return (pick < (unsigned)K) ? (int)pick : 0;                  // no candidate at all only if the residual holds NaNs
 }
 
 // bring-up instrumentation (LYS_TC_TIMING=1): cycles per role/phase, summed over warps (lane 0)
@@ -349,7 +430,7 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                const uint4* __restrict__ planes, const float* __restrict__ Dt, const float* __restrict__ G,
                int K, int nch, int64_t N, int k, int n_units /* clusters */, int rounds,
                int32_t* __restrict__ idx, float* __restrict__ val, int32_t* __restrict__ nsel,
-               float* __restrict__ Z, int64_t zss, float* __restrict__ scratch, int dbg)
+               float* __restrict__ Z, int64_t zss, float* __restrict__ scratch)
 {
     using GE = Geo<PAIR>;
     constexpr int NP = CH / 32;
@@ -631,7 +712,7 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                         for (int sc = 0; sc < NP; sc += 2) {
                             LYS_TMEM_WAIT_X32(b0);
                             LYS_TMEM_LD_X32(ta + (sc + 1) * 32, b1);
-                            if (!(dbg & 4)) scan_piece_r(b0, c * NP + sc, am);
+                            scan_piece_r(b0, c * NP + sc, am);
                             LYS_TMEM_WAIT_X32(b1);
                             if (sc + 2 < NP) LYS_TMEM_LD_X32(ta + (sc + 2) * 32, b0);
                             else {
@@ -639,13 +720,13 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                                 __syncwarp();
                                 if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * (24 + 8 * s + c));
                             }
-                            if (!(dbg & 4)) scan_piece_r(b1, c * NP + sc + 1, am); else am.kept[sc] ^= b0[sc] ^ b1[sc + 1];
+                            scan_piece_r(b1, c * NP + sc + 1, am);
                         }
                         pt.lap(3, lane);
                     }
                     const bool last = (j + 1 >= k);
                     const int run_idx = argmax_finish_r(am);
-                    if (!st.done && !(dbg & 8)) {
+                    if (!st.done) {
                         switch (j) {
 #define LYS_STEP(JJ) case JJ: if constexpr (JJ < KNZ) update_step<JJ, KNZ>(st, run_idx, last, k, Dt, G, K, U, slotA, row); break;
                             LYS_STEP(0) LYS_STEP(1) LYS_STEP(2) LYS_STEP(3) LYS_STEP(4)
@@ -738,7 +819,6 @@ __global__ void prep_dict_kernel(const float* __restrict__ D, int64_t ldd, int n
 
 bool fused_shape_ok(int n, int K, int k)
 {
-    if (const char* e = getenv("LYS_BOMP_PATH")) if (!strcmp(e, "legacy")) return false;
     return n >= 1 && n <= NF && K >= CH && (K % CH) == 0 && K <= 1024 && k >= 1 && k <= 10;
 }
 
@@ -755,8 +835,11 @@ int launch_tc(const float* X, int64_t xfs, int64_t xss, int n, const void* plane
     using GE = Geo<PAIR>;
     const int nch = K / CH;
     const size_t smem = (size_t)nch * GE::B_CHUNK + (size_t)NS * A_SLOT + SMEM_BAR + NS * ZB;
-    static const bool timing = getenv("LYS_TC_TIMING") != nullptr;
-    auto kern = (timing && MODE == 0) ? bomp_tc_kernel<KNZ, PAIR, (MODE == 0), MODE> : bomp_tc_kernel<KNZ, PAIR, false, MODE>;
+#ifdef LYS_BRINGUP      // phase timers: only in the bring-up build (python -m lyssandra_b200._build --bringup)
+    auto kern = bomp_tc_kernel<KNZ, PAIR, (MODE == 0), MODE>;
+#else
+    auto kern = bomp_tc_kernel<KNZ, PAIR, false, MODE>;
+#endif
     LYS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n_tiles = (N + TM - 1) / TM;
     const int64_t tiles_per_unit = (int64_t)PAIR * NS;
@@ -781,8 +864,7 @@ int launch_tc(const float* X, int64_t xfs, int64_t xss, int n, const void* plane
     const int rounds = (int)((n_tiles + (int64_t)units * tiles_per_unit - 1) / ((int64_t)units * tiles_per_unit));
     cfg.gridDim = dim3((unsigned)(units * PAIR), 1, 1);
     LYS_CUDA(cudaLaunchKernelEx(&cfg, kern, X, xfs, xss, n, reinterpret_cast<const uint4*>(planes), Dt, G, K, nch, N, k,
-                                units, rounds, idx, val, nsel, Z, zss, scratch,
-                                getenv("LYS_TC_DBG") ? atoi(getenv("LYS_TC_DBG")) : 0));
+                                units, rounds, idx, val, nsel, Z, zss, scratch));
     LYS_LAUNCH_CHECK("bomp_tc_kernel");
     return LYS_OK;
 }
@@ -809,9 +891,6 @@ int bomp_encode_fused(const float* X, int64_t xfs, int64_t xss, const float* D, 
     unsigned char* planes = reinterpret_cast<unsigned char*>(workspace);
     float* Dt = reinterpret_cast<float*>(planes + align_up(planes_bytes(K), 256));
     float* scratch = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Dt) + align_up(dt_bytes(K), 256));
-    static const int ver = getenv("LYS_TC_VER") ? atoi(getenv("LYS_TC_VER")) : 1;           // bring-up override
-    if (ver == 3 && (K % 128) == 0)
-        return bomp_encode_tc3(X, xfs, xss, D, ldd, G, n, K, N, k, idx, val, nsel, Z, zss, planes, Dt, scratch, stream);
     const int pair = (K > 512) ? 2 : 1;
     const int nch = K / CH;
     const int items = K * (NF / 8);
@@ -843,7 +922,7 @@ int thresh_encode_fused(const float* X, int64_t xfs, int64_t xss, const float* D
                         int n, int K, int64_t N, int k, int32_t* idx, float* val, int32_t* nsel,
                         float* Z, int64_t zas, int64_t zss, void* workspace, size_t workspace_bytes, cudaStream_t stream)
 {
-    if (!fused_shape_ok(n, K, k) || getenv("LYS_THRESH_PATH")) return LYS_EUNSUPPORTED;
+    if (!fused_shape_ok(n, K, k)) return LYS_EUNSUPPORTED;
     if (Z && (zas != 1 || (zss % 4) != 0 || (reinterpret_cast<uintptr_t>(Z) & 15) != 0)) return LYS_EUNSUPPORTED;
     if (workspace_bytes < thresh_fused_workspace_bytes(n, K, N, k)) return LYS_EWORKSPACE;
     unsigned char* planes = reinterpret_cast<unsigned char*>(workspace);
@@ -863,8 +942,9 @@ int thresh_encode_fused(const float* X, int64_t xfs, int64_t xss, const float* D
 
 }  // namespace lys
 
-// bring-up hook (not part of the documented ABI): cycles per phase accumulated by kernels launched
-// with LYS_TC_TIMING set; reading resets the counters
+#ifdef LYS_BRINGUP
+// bring-up hooks (not part of the ABI, compiled only with -DLYS_BRINGUP): cycles per phase accumulated by the
+// instrumented kernels; reading resets the counters
 extern "C" __attribute__((visibility("default"))) int lys_debug_tc_timing(unsigned long long* out16)
 {
     cudaDeviceSynchronize();
@@ -883,3 +963,4 @@ extern "C" __attribute__((visibility("default"))) int lys_debug_tc_trace(unsigne
     if (cudaMemcpyToSymbol(lys::g_tc_trace_n, &z, sizeof(z)) != cudaSuccess) return -2;
     return 0;
 }
+#endif  // LYS_BRINGUP

@@ -71,7 +71,7 @@ bomp_warp_kernel(const float* __restrict__ alpha, const float* __restrict__ G,
                 int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
                 if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
             }
-            const int pick = bidx;
+            const int pick = (bidx < K) ? bidx : 0;      // no maximum only if alpha holds NaNs (np.argmax would return the first NaN): stay in range
             // ---- :323-325 already selected -> stop
             bool dup = false;
             for (int m = 0; m < cnt; ++m) dup |= (ws->I[m] == pick);

@@ -1,8 +1,8 @@
-// comm.cu — peer-mapped exchange buffers for the multi-rank K-SVD sweep (one process per GPU).
-// Each rank cudaMalloc's one small buffer, exports its CUDA IPC handle (64 bytes); the host
+// comm.cu — peer-mapped mailboxes for the multi-rank K-SVD sweep (one process per GPU).
+// Each rank cudaMalloc's one buffer (2.2 MB), exports its CUDA IPC handle (64 bytes); the host
 // (torch.distributed all_gather) hands every rank all handles; peers are opened with
 // cudaIpcOpenMemHandle, which maps them over NVLink/NVSwitch.  The sweep kernel then writes its
-// per-atom partial sums straight into every peer's buffer and polls flags in its own.
+// per-atom sums straight into every peer's mailbox as tagged 8-byte words (comm.cuh).
 #include "comm.cuh"
 #include <string.h>
 
@@ -49,11 +49,8 @@ extern "C" int lys_comm_connect(void* comm, const unsigned char* all_handles)
         LYS_CUDA(cudaIpcOpenMemHandle(&h->peer[r], ipc, cudaIpcMemLazyEnablePeerAccess));
     }
     h->dev.rank = h->rank; h->dev.world = h->world;
-    for (int r = 0; r < COMM_MAX_RANKS; ++r) {
-        void* base = r < h->world ? h->peer[r] : nullptr;
-        h->dev.slots[r] = reinterpret_cast<float*>(base);
-        h->dev.flags[r] = base ? reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(base) + COMM_FLAG_OFFSET_BYTES) : nullptr;
-    }
+    for (int r = 0; r < COMM_MAX_RANKS; ++r)
+        h->dev.box[r] = reinterpret_cast<unsigned long long*>(r < h->world ? h->peer[r] : nullptr);
     h->connected = true;
     return LYS_OK;
 }

@@ -1,55 +1,63 @@
-// ksvd_sweep.cu — the atom loop of approximate K-SVD (lyssa/dict_learning/ksvd.py:105-124) as ONE
-// persistent cooperative kernel, fused with its per-atom reduction across CTAs and, when the
-// signals are sharded over GPUs, across ranks (peer-mapped NVLink buffers, no host round trip).
+// ksvd_sweep.cu — the atom loop of approximate K-SVD (lyssa/dict_learning/ksvd.py:105-124) as ONE persistent
+// cooperative kernel per cycle, fused with its per-atom reduction across CTAs and, when the signals are sharded over
+// GPUs, across ranks (peer-mapped NVLink mailboxes, no host round trip).
 //
-// Per atom c (sequential, Gauss-Seidel order is part of the reference's result):
+// Per atom c (sequential; the Gauss-Seidel order is part of the reference's result):
 //     users = columns with Z[c,:] != 0                      :111   (CSR built by lys_build_atom_csr)
 //     s  = R[:,users] x + d (x.x)          == R_k x         :116-118   (R_k never materialised)
 //     d' = s / (||s|| + eps)                                :119
 //     x' = R[:,users]^T d' + x (d.d')      == R_k^T d'      :121
 //     R[:,users] += d x^T - d' x'^T        == R_k - d' x'   :123
-// Ownership: CTA b owns the contiguous signal range [b*S, (b+1)*S).  The users of an atom are
-// sorted by signal, so each CTA's users form one sub-range of the CSR segment (`bounds`,
-// precomputed by binary search).  Because a residual row is only ever touched by its owner CTA,
-// the only device-wide dependency per atom is the (n+1)-float sum s, sxx:
-//     phase 1 (users' rows -> registers, partial sums) -> per-CTA partial + release flag
-//     -> every CTA polls the flags of all CTAs (barrier and data fetch in one L2 round trip)
-//     -> fixed-order two-level sum (deterministic, replicated) [-> rank exchange] -> d'
-//     -> phase 2 from the register-resident rows -> next atom.   ONE grid-wide sync per atom.
-// Multi-rank: CTA 0 writes the rank's (n+2) floats (s, sxx, user count) into every peer's slot
-// and raises its flag there (st.release.sys over NVLink); all CTAs poll their own rank's flags
-// and sum the slots in rank order, so every rank computes bit-identical d'.
+// The only device-wide dependency is the sum s (n floats), x.x and the user count of every atom: 1024 dependent
+// all-reduces per sweep at cfg3.  Two things keep that chain short.
+//
+// (1) Look-ahead by one atom (exact).  The sums of atom c+1 are taken over R BEFORE atom c has been applied, together
+//     with the terms that turn them into the sums over the updated R once d'_c is known.  With S = sum_i R_i x_{c+1,i}
+//     over the users of c+1, T the same sum restricted to the signals that use BOTH c and c+1, and a = sum over
+//     those signals of x_{c,i} x_{c+1,i} (old coefficients):
+//         x'_{c,i} = R_i.d'_c + x_{c,i} g,  g = d_c.d'_c          (:121)
+//         sum_i R^{new}_i x_{c+1,i} = S + d_c a - d'_c (d'_c.T + g a)
+//     so the partial sums of atom c+1 are published before the reduction of atom c has even been read, and the
+//     reduction latency (L2 round trips, NVLink hops) overlaps the row updates of the previous atom.  Which users
+//     of c+1 also use c is precomputed per code entry (`link`, one byte: the slot of atom c in the same signal).
+// (2) The reduction is integer arithmetic.  Every CTA converts its partial sums to fixed point (scale chosen from
+//     ||R||_F and ||val||_2 so that no sum can overflow) and adds them into one 64-bit word per element with
+//     red.global.add.u64; the low 8 bits of the word count the contributions, so a reader spins on the word itself
+//     until all CTAs have added — no flags, no fences, no second round trip — and the result does not depend on the
+//     order of the additions: the sweep is bitwise reproducible and every rank computes bit-identical atoms.
+//     Residual rows and coefficients are private to the CTA that owns the signal (CTA b owns [b*S, (b+1)*S); the
+//     users of an atom are sorted by signal, so its users are one sub-range of the CSR segment, `bounds`), hence
+//     nothing else is ever communicated.
+// Multi-rank: one warp of every CTA forwards the completed local sums of "its" atoms (atom c -> CTA c mod grid)
+// into every peer's mailbox as tagged 8-byte words (comm.cuh); readers add the peers' words to their own sum.
 #include "comm.cuh"
 #include <algorithm>
+#include <cmath>
 
 namespace lys {
 namespace {
 
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p)
+using u64 = unsigned long long;
+
+__device__ __forceinline__ u64 ld_relaxed_gpu(const u64* p)
 {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v)
+__device__ __forceinline__ u64 ld_relaxed_sys(const u64* p)
 {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
-{
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    u64 v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
+__device__ __forceinline__ void st_relaxed_sys(u64* p, u64 v)
 {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ float ld_volatile_f32(const float* p)
+__device__ __forceinline__ void red_add(u64* p, u64 v)
 {
-    float v;
-    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-    return v;
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 // bounds[c][b] = first CSR position of atom c whose signal is >= b*S   (b = 0..G), bounds[c][G] = rowptr[c+1]
@@ -68,6 +76,58 @@ __global__ void sweep_bounds_kernel(const int32_t* __restrict__ rowptr, const in
     bounds[id] = lo;
 }
 
+// link[i*k + s] = slot of atom (idx[i][s] - 1) in the code of signal i, or 255 (both entries must be users, ksvd.py:111)
+__global__ void sweep_link_kernel(const int32_t* __restrict__ idx, const float* __restrict__ val, int64_t N, int k,
+                                  uint8_t* __restrict__ link)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int32_t* row = idx + i * k;
+    const float* vrow = val + i * k;
+    for (int s = 0; s < k; ++s) {
+        const int a = row[s];
+        int lk = 255;
+        if (a >= 1 && vrow[s] != 0.f) {
+            for (int s2 = k - 1; s2 >= 0; --s2)
+                if (row[s2] == a - 1 && vrow[s2] != 0.f) lk = s2;
+        }
+        link[i * k + s] = (uint8_t)lk;
+    }
+}
+
+// fixed-point scale of the sweep's sums: every partial sum is bounded by ||val|| max(||R||_F, ||val||) (Cauchy-Schwarz),
+// summed over the ranks; fx = 2^e with |sum| fx <= 2^45 leaves 2^10 of headroom in the 55-bit field for the growth of
+// the norms during the sweep.  All ranks must use the same scale: the bounds are exchanged through the mailboxes.
+__global__ void sweep_scale_kernel(const double* __restrict__ fro /* ||R||^2, ||val||^2 */, double* __restrict__ fx_out,
+                                   PeerComm pc, unsigned gen)
+{
+    const int lane = threadIdx.x;
+    const double r = sqrt(fro[0]), v = sqrt(fro[1]);
+    float bound = (float)(v * fmax(r, v) * 1.000001);
+    if (!(bound >= 0.f)) bound = 3.0e38f;
+    if (pc.world > 1) {
+        const u64 tag = comm_tag(gen);
+        if (lane < pc.world && lane != pc.rank)
+            st_relaxed_sys(pc.box[lane] + comm_word(COMM_WINDOW, pc.rank, 0), ((u64)__float_as_uint(bound) << 16) | tag);
+        float other = 0.f;
+        if (lane < pc.world && lane != pc.rank) {
+            const u64* w = pc.box[pc.rank] + comm_word(COMM_WINDOW, lane, 0);
+            u64 x;
+            do { x = ld_relaxed_sys(w); } while ((x & 0xFFFFull) != tag);
+            other = __uint_as_float((unsigned)(x >> 16));
+        }
+        bound = fmaxf(bound, other);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bound = fmaxf(bound, __shfl_xor_sync(0xffffffffu, bound, o));
+        bound *= (float)pc.world;
+    }
+    if (lane == 0) {
+        double fx = 1.0;
+        if (bound > 0.f && bound < 3.0e38f) fx = exp2(45.0 - ceil(log2((double)bound)));
+        fx_out[0] = fx;
+    }
+}
+
 // entry id -> signal index: ent / k by multiply-shift (k <= 32, ent < 2^31; M = ceil(2^(32+s)/k) is exact
 // for every 32-bit numerator because M*k - 2^(32+s) < k <= 2^s)
 struct FastDiv { unsigned long long M; int s; };
@@ -76,303 +136,407 @@ __device__ __forceinline__ int fdiv(int ent, FastDiv d)
     return (int)(((unsigned long long)(unsigned)ent * d.M) >> (32 + d.s));
 }
 
-constexpr int SW_WARPS = 16;
-constexpr int SW_U = 12;         // users per warp whose ids/coefficients/rows stay in registers (192 per CTA)
+// 16 warps per CTA (one CTA per SM, 128 registers per thread).  Multi-rank: warp 15 forwards, 15 warps compute.
+constexpr int SW_THREADS = 512;
+template <int CW> __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CW * 32) : "memory"); }
 
-// ids of this warp's users of one atom (issued a whole atom ahead) ...
-__device__ __forceinline__ void load_user_ids(const int32_t* __restrict__ entries, int lo, int hi, int warp,
-                                              int (&ent)[SW_U])
+struct SweepArgs {
+    float* R; const float* Dt; float* Dt_new; float* val;
+    const int32_t* entries; const uint8_t* link; const int32_t* bounds;
+    int n, K, k, lda, acc_stride;
+    int32_t* unused;
+    u64* acc;                     // [K][lda] words, acc_stride words apart, zeroed before the launch
+    const double* fx;
+    PeerComm pc; unsigned gen0;   // mailbox generation of atoms [0, COMM_WINDOW)
+    FastDiv kdiv;
+};
+
+// the users of one atom that one warp keeps in registers: lane u holds user u
+struct UserSet { int ent; float x; int lk; float xp; };
+struct Range { int p0, nu, ovf, hi, cnt; };
+
+template <int CW>
+__device__ __forceinline__ Range make_range(int lo, int hi, int warp, int U)
 {
-#pragma unroll
-    for (int u = 0; u < SW_U; ++u) {
-        const int p = lo + warp + u * SW_WARPS;
-        ent[u] = (p < hi) ? __ldg(entries + p) : -1;
-    }
+    Range r;
+    r.cnt = hi - lo;
+    const int pw = min(U, (r.cnt + CW - 1) / CW);
+    r.p0 = lo + warp * pw;
+    r.nu = max(0, min(pw, hi - r.p0));
+    r.ovf = lo + CW * pw;              // users beyond CW * U per CTA and atom are streamed, not kept
+    r.hi = hi;
+    return r;
 }
-// ... and their coefficients + an L2 prefetch of their residual rows.  Safe while the previous atom
-// is still in flight: an atom's coefficients are only written by that atom's own phase 2, and the
-// rows are only PREFETCHED here (they are re-read after the previous atom's phase 2).
-__device__ __forceinline__ void load_user_coefs(const float* val, const float* R, int lane, int n, FastDiv k,
-                                                const int (&ent)[SW_U], float (&x)[SW_U])
+
+// ids, coefficients, links of a warp's users + an L2 prefetch of their residual rows.  Issued two atoms ahead: an atom's
+// coefficients are only written by that atom's own phase 2, and the linked coefficient (atom c-1 in the same signal) is
+// read before phase 2 of c-1 of THIS sweep can have run only if ... it has not: the set of atom c+2 is loaded during
+// iteration c, phase 2 of atom c+1 runs in iteration c+1.
+__device__ __forceinline__ UserSet load_set(const SweepArgs& a, const Range& rg, int lane)
+{
+    UserSet s;
+    s.ent = -1; s.x = 0.f; s.lk = 255; s.xp = 0.f;
+    if (lane < rg.nu) {
+        s.ent = __ldg(a.entries + rg.p0 + lane);
+        s.x = __ldcg(a.val + s.ent);
+        s.lk = __ldg(a.link + s.ent);
+        const int i = fdiv(s.ent, a.kdiv);
+        if (s.lk != 255) s.xp = __ldcg(a.val + (int64_t)i * a.k + s.lk);
+        const char* row = reinterpret_cast<const char*>(a.R + (int64_t)i * a.n);
+        for (int off = 0; off < a.n * 4; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off));
+    }
+    return s;
+}
+
+template <int NPL, int U>
+__device__ __forceinline__ void load_rows(const SweepArgs& a, const UserSet& s, int nu, int lane, float (&rv)[U][NPL])
 {
 #pragma unroll
-    for (int u = 0; u < SW_U; ++u) {
-        x[u] = 0.f;
-        if (ent[u] >= 0) {
-            x[u] = val[ent[u]];
-            const char* row = reinterpret_cast<const char*>(R + (int64_t)fdiv(ent[u], k) * n);
-            if (lane * 128 < n * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + lane * 128));
+    for (int u = 0; u < U; ++u) {
+        const int e = __shfl_sync(0xffffffffu, s.ent, u);
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) rv[u][q] = 0.f;
+        if (u < nu) {
+            const float* r = a.R + (int64_t)fdiv(e, a.kdiv) * a.n;
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) { const int f = lane + 32 * q; if (f < a.n) rv[u][q] = __ldcg(r + f); }
         }
     }
 }
 
-template <int NPL>
-__global__ void __launch_bounds__(SW_WARPS * 32, 1)
-ksvd_sweep_kernel(float* __restrict__ R, float* __restrict__ Dt, float* __restrict__ val,
-                  const int32_t* __restrict__ rowptr, const int32_t* __restrict__ entries,
-                  const int32_t* __restrict__ bounds,
-                  int n, int K, int k, int n_cycles,
-                  int32_t* __restrict__ unused,
-                  float* __restrict__ partial /* [2][grid][n+1] */, unsigned* __restrict__ flags /* [2][grid] */,
-                  PeerComm pc, unsigned comm_seq0, FastDiv kdiv)
+// partial sums of one atom over this CTA's users (rows as they are NOW), added into the atom's accumulators
+template <int NPL, int U, int CW>
+__device__ __forceinline__ void publish_atom(const SweepArgs& a, int c, const UserSet& s, const Range& rg,
+                                             const float (&rv)[U][NPL], float* red, double fx, int tid, int lane, int warp)
 {
+    const int n = a.n, lda = a.lda;
+    float S[NPL], T[NPL];
+#pragma unroll
+    for (int q = 0; q < NPL; ++q) { S[q] = 0.f; T[q] = 0.f; }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const float x = __shfl_sync(0xffffffffu, s.x, u);
+        const bool linked = __shfl_sync(0xffffffffu, s.lk, u) != 255;
+        if (u < rg.nu) {
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) S[q] = fmaf(rv[u][q], x, S[q]);
+            if (linked) {
+#pragma unroll
+                for (int q = 0; q < NPL; ++q) T[q] = fmaf(rv[u][q], x, T[q]);
+            }
+        }
+    }
+    float xx = (lane < rg.nu) ? s.x * s.x : 0.f;
+    float aa = (lane < rg.nu && s.lk != 255) ? s.xp * s.x : 0.f;
+    for (int p = rg.ovf + warp; p < rg.hi; p += CW) {                 // streamed users (only for very popular atoms)
+        const int e = __ldg(a.entries + p);
+        const float xo = __ldcg(a.val + e);
+        const int lk = __ldg(a.link + e);
+        const int i = fdiv(e, a.kdiv);
+        const float* r = a.R + (int64_t)i * n;
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) {
+            const int f = lane + 32 * q;
+            const float rvv = (f < n) ? __ldcg(r + f) : 0.f;
+            S[q] = fmaf(rvv, xo, S[q]);
+            if (lk != 255) T[q] = fmaf(rvv, xo, T[q]);
+        }
+        if (lane == 0) {
+            xx = fmaf(xo, xo, xx);
+            if (lk != 255) aa = fmaf(__ldcg(a.val + (int64_t)i * a.k + lk), xo, aa);
+        }
+    }
+    xx = warp_sum(xx);
+    aa = warp_sum(aa);
+    float* mine = red + warp * lda;
+#pragma unroll
+    for (int q = 0; q < NPL; ++q) {
+        const int f = lane + 32 * q;
+        if (f < n) { mine[f] = S[q]; mine[n + f] = T[q]; }
+    }
+    if (lane == 0) { mine[2 * n] = aa; mine[2 * n + 1] = xx; }
+    compute_sync<CW>();
+    for (int t = tid; t < lda; t += CW * 32) {
+        long long q;
+        if (t < 2 * n + 2) {
+            double sum = 0.0;
+#pragma unroll
+            for (int w = 0; w < CW; ++w) sum += (double)red[w * lda + t];
+            q = __double2ll_rn(sum * fx);
+        } else {
+            q = (long long)rg.cnt << 8;                                 // user count: exact, survives the 48-bit forward
+        }
+        red_add(a.acc + ((size_t)c * lda + t) * a.acc_stride, ((u64)q << 8) + 1ull);
+    }
+}
+
+template <int NPL, bool MULTI>
+__global__ void __launch_bounds__(SW_THREADS, 1)
+ksvd_sweep_kernel(const SweepArgs a)
+{
+    constexpr int U = (NPL <= 2) ? 16 : 32 / NPL;
+    constexpr int CW = MULTI ? 15 : 16;            // compute warps
     extern __shared__ float sm[];
-    float* d_old = sm;                       // [n]
-    float* d_new = d_old + n;                // [n]
-    float* svec = d_new + n;                 // [n + 2]
-    float* red = svec + (n + 2);             // [max(SW_WARPS, groups)][n + 1]
-    __shared__ float s_g;
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int ldr = n + 1;
+    float* svec = sm;                         // [lda]   the reduced sums of the current atom
+    float* red = svec + a.lda;                // [CW][lda]
+    __shared__ int s_progress;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = a.n, K = a.K, lda = a.lda;
     const int G = gridDim.x, b = blockIdx.x;
-    const int groups = (SW_WARPS * 32) / ldr;
-    unsigned seq = 0;
+    const double fx = a.fx[0];
 
-    for (int cyc = 0; cyc < n_cycles; ++cyc) {
-        // Software pipeline over atoms: the ids/coefficients of atom c+1's users and this CTA's CSR
-        // bounds of atom c+2 are loaded while atom c is in flight, so no dependent address chain
-        // (bounds -> ids -> coefficients -> rows) sits on the per-atom critical path.  Every atom runs
-        // the same protocol; an atom nobody uses (ksvd.py:112-115) is detected from the summed user
-        // count and only skips the refresh (rare, so the wasted sync does not matter).
-        int ent[SW_U]; float x[SW_U];
-        int lo = bounds[b], hi = bounds[b + 1];
-        int lo2 = 0, hi2 = 0;
-        if (K > 1) { lo2 = bounds[(G + 1) + b]; hi2 = bounds[(G + 1) + b + 1]; }
-        load_user_ids(entries, lo, hi, warp, ent);
-        load_user_coefs(val, R, lane, n, kdiv, ent, x);
+    if (tid == 0) s_progress = -1;
+    __syncthreads();
 
-        for (int c = 0; c < K; ++c) {
-            const int local_count = rowptr[c + 1] - rowptr[c];
-            ++seq;
-            const int par = seq & 1;
-            // ---- rows of this CTA's users: issued first (L2 hits after the prefetch)
-            float rv[SW_U][NPL];
+    if (MULTI && warp == CW) {
+        // ---------------------------------------------------------------- forwarder (one warp, atoms c = b, b+G, ...)
+        volatile int* progress = &s_progress;
+        for (int c = b; c < K; c += G) {
+            while (*progress < c - 2) __nanosleep(400);
+            const u64 tag = comm_tag(a.gen0 + (unsigned)(c / COMM_WINDOW));
+            for (int t = lane; t < lda; t += 32) {
+                const u64* w = a.acc + ((size_t)c * lda + t) * a.acc_stride;
+                u64 v;
+                while (((v = ld_relaxed_gpu(w)) & 255ull) != (u64)G) __nanosleep(40);
+                const u64 payload = ((v - (u64)G) & ~0xFFFFull) | tag;      // high 48 bits of the local sum
+                for (int r = 0; r < a.pc.world; ++r)
+                    if (r != a.pc.rank) st_relaxed_sys(a.pc.box[r] + comm_word(c % COMM_WINDOW, a.pc.rank, t), payload);
+            }
+        }
+        return;
+    }
+
+    // -------------------------------------------------------------------------------- compute warps
+    const int32_t* bnd = a.bounds + b;
+    auto bound_of = [&](int c, int& lo, int& hi) {
+        lo = 0; hi = 0;
+        if (c < K) { lo = __ldg(bnd + (size_t)c * (G + 1)); hi = __ldg(bnd + (size_t)c * (G + 1) + 1); }
+    };
+    int lo, hi;
+    bound_of(0, lo, hi);
+    Range rgC = make_range<CW>(lo, hi, warp, U);
+    bound_of(1, lo, hi);
+    Range rgN = make_range<CW>(lo, hi, warp, U);
+    int lo2, hi2;
+    bound_of(2, lo2, hi2);
+    UserSet setC = load_set(a, rgC, lane);
+    UserSet setN = load_set(a, rgN, lane);
+    float rvC[U][NPL], rvN[U][NPL];
+    load_rows<NPL, U>(a, setC, rgC.nu, lane, rvC);
+    publish_atom<NPL, U, CW>(a, 0, setC, rgC, rvC, red, fx, tid, lane, warp);
+    compute_sync<CW>();                           // `red` is rewritten by the first look-ahead below
+
+    float dold[NPL], doldN[NPL], dnP[NPL], doldP[NPL];
+    float gP = 0.f;
 #pragma unroll
-            for (int u = 0; u < SW_U; ++u) {
+    for (int q = 0; q < NPL; ++q) {
+        const int f = lane + 32 * q;
+        dold[q] = (f < n) ? __ldg(a.Dt + f) : 0.f;
+        dnP[q] = 0.f; doldP[q] = 0.f; doldN[q] = 0.f;
+    }
+
+    for (int c = 0; c < K; ++c) {
+        if (tid == 0) *reinterpret_cast<volatile int*>(&s_progress) = c;
+        // ---- rows of atom c that atom c-1 has just rewritten (its users were loaded before that update)
+        {
+            const unsigned stale = __ballot_sync(0xffffffffu, lane < rgC.nu && setC.lk != 255);
+            if (stale) {
 #pragma unroll
-                for (int q = 0; q < NPL; ++q) rv[u][q] = 0.f;
-                if (ent[u] >= 0) {
-                    const float* r = R + (int64_t)fdiv(ent[u], kdiv) * n;
+                for (int u = 0; u < U; ++u) {
+                    if ((stale >> u) & 1u) {
+                        const int e = __shfl_sync(0xffffffffu, setC.ent, u);
+                        const float* r = a.R + (int64_t)fdiv(e, a.kdiv) * n;
 #pragma unroll
-                    for (int q = 0; q < NPL; ++q) { const int f = lane + 32 * q; if (f < n) rv[u][q] = r[f]; }
+                        for (int q = 0; q < NPL; ++q) { const int f = lane + 32 * q; if (f < n) rvC[u][q] = __ldcg(r + f); }
+                    }
                 }
             }
-            for (int f = t; f < n; f += blockDim.x) d_old[f] = Dt[(int64_t)c * n + f];
-            // ---- next atom's user ids (its bounds are already in registers), bounds of atom c+2
-            int ent2[SW_U]; float x2n[SW_U];
-            if (c + 1 < K) {
-                load_user_ids(entries, lo2, hi2, warp, ent2);
+        }
+        // ---- two atoms ahead: ids / coefficients / links + L2 prefetch of the rows; three ahead: CSR bounds
+        const Range rgP = make_range<CW>(lo2, hi2, warp, U);
+        const UserSet setP = load_set(a, rgP, lane);
+        bound_of(c + 3, lo2, hi2);
+        if (c + 1 < K) {
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) { const int f = lane + 32 * q; doldN[q] = (f < n) ? __ldg(a.Dt + (size_t)(c + 1) * n + f) : 0.f; }
+            // ---- look-ahead: sums of atom c+1 over the rows as they are before atom c is applied
+            load_rows<NPL, U>(a, setN, rgN.nu, lane, rvN);
+            publish_atom<NPL, U, CW>(a, c + 1, setN, rgN, rvN, red, fx, tid, lane, warp);
+        }
+        // ---- reduced sums of atom c (published one iteration ago)
+        for (int t = tid; t < lda; t += CW * 32) {
+            const u64* w = a.acc + ((size_t)c * lda + t) * a.acc_stride;
+            u64 v;
+            do { v = ld_relaxed_gpu(w); } while ((v & 255ull) != (u64)G);
+            long long q;
+            if (!MULTI) {
+                q = (long long)(v - (u64)G) >> 8;
             } else {
-#pragma unroll
-                for (int u = 0; u < SW_U; ++u) ent2[u] = -1;
-            }
-            int lo3 = 0, hi3 = 0;
-            if (c + 2 < K) { lo3 = bounds[(c + 2) * (G + 1) + b]; hi3 = bounds[(c + 2) * (G + 1) + b + 1]; }
-
-            // ---- phase 1: partial s = sum_i R[i,:] x_i, sxx = sum x_i^2         (ksvd.py:116-118)
-            float acc[NPL];
-#pragma unroll
-            for (int q = 0; q < NPL; ++q) acc[q] = 0.f;
-            float sxx = 0.f;
-#pragma unroll
-            for (int u = 0; u < SW_U; ++u) {
-#pragma unroll
-                for (int q = 0; q < NPL; ++q) acc[q] = fmaf(rv[u][q], x[u], acc[q]);
-                sxx = fmaf(x[u], x[u], sxx);
-            }
-            for (int p = lo + warp + SW_U * SW_WARPS; p < hi; p += SW_WARPS) {       // overflow users (rare)
-                const int e2 = entries[p];
-                const float xo = val[e2];
-                const float* r = R + (int64_t)fdiv(e2, kdiv) * n;
-#pragma unroll
-                for (int q = 0; q < NPL; ++q) { const int f = lane + 32 * q; if (f < n) acc[q] = fmaf(r[f], xo, acc[q]); }
-                sxx = fmaf(xo, xo, sxx);
-            }
-#pragma unroll
-            for (int q = 0; q < NPL; ++q) { const int f = lane + 32 * q; if (f < n) red[warp * ldr + f] = acc[q]; }
-            if (lane == 0) red[warp * ldr + n] = sxx;
-            __syncthreads();
-            float* my_partial = partial + ((size_t)par * G + b) * ldr;
-            if (t <= n) {
-                double s = 0.0;
-                for (int w = 0; w < SW_WARPS; ++w) s += (double)red[w * ldr + t];
-                my_partial[t] = (float)s;
-            }
-            __syncthreads();
-            if (t == 0) { __threadfence(); st_release_gpu(flags + (size_t)par * G + b, seq); }
-
-            // ---- overlap with the grid converging: coefficients + row prefetch of the next atom
-            load_user_coefs(val, R, lane, n, kdiv, ent2, x2n);
-
-            // ---- grid-wide: wait for every CTA's partial (flag poll = barrier + data-ready in one)
-            for (int tt = t; tt < G; tt += blockDim.x) { while (ld_acquire_gpu(flags + (size_t)par * G + tt) != seq) { } }
-            __syncthreads();
-            if (t < groups * ldr) {
-                const int f = t % ldr, g = t / ldr;
-                const float* src = partial + (size_t)par * G * ldr + f;
-                double s = 0.0;
-                for (int b0 = g; b0 < G; b0 += 24 * groups) {         // up to 24 independent L2 loads in flight
-                    float v[24];
-#pragma unroll
-                    for (int q = 0; q < 24; ++q) { const int bb = b0 + q * groups; v[q] = (bb < G) ? __ldcg(src + (size_t)bb * ldr) : 0.f; }
-#pragma unroll
-                    for (int q = 0; q < 24; ++q) s += (double)v[q];     // fixed order: deterministic
+                q = (long long)(v - (u64)G) >> 16;
+                const u64 tag = comm_tag(a.gen0 + (unsigned)(c / COMM_WINDOW));
+                for (int r = 0; r < a.pc.world; ++r) {
+                    if (r == a.pc.rank) continue;
+                    const u64* m = a.pc.box[a.pc.rank] + comm_word(c % COMM_WINDOW, r, t);
+                    u64 x;
+                    do { x = ld_relaxed_sys(m); } while ((x & 0xFFFFull) != tag);
+                    q += (long long)x >> 16;
                 }
-                red[g * ldr + f] = (float)s;
             }
-            __syncthreads();
-            if (t <= n) {
-                double s = 0.0;
-                for (int g = 0; g < groups; ++g) s += (double)red[g * ldr + t];
-                svec[t] = (float)s;
-            }
-            if (t == n + 1) svec[n + 1] = (float)local_count;
-            __syncthreads();
-            // ---- rank exchange over peer-mapped buffers (only when the signals are sharded)
-            if (pc.world > 1) {
-                const unsigned cseq = comm_seq0 + seq;
-                if (b == 0) {
-                    if (t <= n + 1) {
-                        const float v = svec[t];
-                        for (int r = 0; r < pc.world; ++r) pc.slots[r][((size_t)par * COMM_MAX_RANKS + pc.rank) * COMM_LD + t] = v;
-                    }
-                    __syncthreads();
-                    if (t < pc.world) {
-                        __threadfence_system();
-                        st_release_sys(pc.flags[t] + par * COMM_MAX_RANKS + pc.rank, cseq);
-                    }
-                }
-                if (t < pc.world) { while (ld_acquire_sys(pc.flags[pc.rank] + par * COMM_MAX_RANKS + t) != cseq) { } }
-                __syncthreads();
-                if (t <= n + 1) {
-                    double s = 0.0;
-                    for (int r = 0; r < pc.world; ++r)
-                        s += (double)ld_volatile_f32(pc.slots[pc.rank] + ((size_t)par * COMM_MAX_RANKS + r) * COMM_LD + t);
-                    svec[t] = (float)s;
-                }
-                __syncthreads();
-            }
-            const bool atom_used = svec[n + 1] != 0.f;            // uniform over CTAs and ranks
-            if (!atom_used && b == 0 && t == 0) unused[c] = 1;
-            __syncwarp();      // reconverge warp 0 before the next bar.sync (racecheck finding)
-            if (atom_used) {
-                // ---- new atom                                                    (ksvd.py:118-119)
-                if (warp == 0) {
-                    const float sxx_all = svec[n];
-                    float sv[NPL], dsq = 0.f;
+            const double scale = (t < 2 * n + 2) ? (MULTI ? 256.0 : 1.0) / fx : (MULTI ? 1.0 : 1.0 / 256.0);
+            svec[t] = (float)((double)q * scale);
+        }
+        compute_sync<CW>();
+        // ---- new atom (every warp computes it redundantly: no second barrier)          (ksvd.py:118-119)
+        const float aa = svec[2 * n], sxx = svec[2 * n + 1];
+        const bool used = svec[2 * n + 2] != 0.f;                     // uniform over CTAs and ranks
+        float dn[NPL], sv[NPL], tv[NPL];
+        float dT = 0.f;
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) {
+            const int f = lane + 32 * q;
+            sv[q] = (f < n) ? svec[f] : 0.f;
+            tv[q] = (f < n) ? svec[n + f] : 0.f;
+            dT = fmaf(dnP[q], tv[q], dT);
+        }
+        dT = warp_sum(dT);
+        const float coef = fmaf(gP, aa, dT);                          // sum over shared users of x'_{c-1,i} x_{c,i}
+        float dsq = 0.f;
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) {
+            sv[q] = fmaf(dold[q], sxx, fmaf(-dnP[q], coef, fmaf(doldP[q], aa, sv[q])));      // R_k x = R x + d (x.x)
+            dsq = fmaf(sv[q], sv[q], dsq);
+        }
+        dsq = warp_sum(dsq);
+        const float inv = 1.f / (sqrtf(dsq) + kRefEps);              // utils/math.py:61-62
+        float g = 0.f;
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) {
+            dn[q] = used ? sv[q] * inv : dold[q];                    // an atom nobody uses is left alone (:112-115)
+            g = fmaf(dold[q], dn[q], g);
+        }
+        g = warp_sum(g);
+        if (b == 0 && warp == 0) {
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) { const int f = lane + 32 * q; if (f < n) a.Dt_new[(size_t)c * n + f] = dn[q]; }
+            if (!used && lane == 0) a.unused[c] = 1;
+        }
+        // ---- phase 2: x' = R_k^T d' ; R <- R_k - d' x'                                  (ksvd.py:121-123)
+        if (used) {
+            float xnew = 0.f;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const float x = __shfl_sync(0xffffffffu, setC.x, u);
+                const int e = __shfl_sync(0xffffffffu, setC.ent, u);
+                if (u < rgC.nu) {
+                    float dot = 0.f;
+#pragma unroll
+                    for (int q = 0; q < NPL; ++q) dot = fmaf(rvC[u][q], dn[q], dot);
+                    dot = warp_sum(dot);
+                    const float xn = fmaf(x, g, dot);
+                    float* r = a.R + (int64_t)fdiv(e, a.kdiv) * n;
 #pragma unroll
                     for (int q = 0; q < NPL; ++q) {
                         const int f = lane + 32 * q;
-                        sv[q] = (f < n) ? fmaf(d_old[f], sxx_all, svec[f]) : 0.f;     // R_k x = R x + d (x.x)
-                        dsq = fmaf(sv[q], sv[q], dsq);
+                        if (f < n) __stcg(r + f, fmaf(-dn[q], xn, fmaf(dold[q], x, rvC[u][q])));
                     }
-                    dsq = warp_sum(dsq);
-                    const float inv = 1.f / (sqrtf(dsq) + kRefEps);                    // utils/math.py:61-62
-                    float g = 0.f;
-#pragma unroll
-                    for (int q = 0; q < NPL; ++q) {
-                        const int f = lane + 32 * q;
-                        if (f < n) {
-                            const float dnv = sv[q] * inv;
-                            d_new[f] = dnv;
-                            g = fmaf(d_old[f], dnv, g);
-                            if (b == 0) Dt[(int64_t)c * n + f] = dnv;
-                        }
-                    }
-                    g = warp_sum(g);
-                    if (lane == 0) s_g = g;
+                    if (lane == u) xnew = xn;
                 }
-                __syncthreads();
-                const float g = s_g;
-                // ---- phase 2: x' = R_k^T d' ; R <- R_k - d' x'                  (ksvd.py:121-123)
-                float dn[NPL], dold[NPL];
+            }
+            if (lane < rgC.nu) __stcg(a.val + setC.ent, xnew);
+            for (int p = rgC.ovf + warp; p < rgC.hi; p += CW) {
+                const int e = __ldg(a.entries + p);
+                const float xo = __ldcg(a.val + e);
+                float* r = a.R + (int64_t)fdiv(e, a.kdiv) * n;
+                float r2[NPL], dot = 0.f;
 #pragma unroll
                 for (int q = 0; q < NPL; ++q) {
                     const int f = lane + 32 * q;
-                    dn[q] = (f < n) ? d_new[f] : 0.f;
-                    dold[q] = (f < n) ? d_old[f] : 0.f;
+                    r2[q] = (f < n) ? __ldcg(r + f) : 0.f;
+                    dot = fmaf(r2[q], dn[q], dot);
                 }
+                dot = warp_sum(dot);
+                const float xn = fmaf(xo, g, dot);
 #pragma unroll
-                for (int u = 0; u < SW_U; ++u) {
-                    if (ent[u] >= 0) {                               // warp-uniform
-                        float dot = 0.f;
-#pragma unroll
-                        for (int q = 0; q < NPL; ++q) dot = fmaf(rv[u][q], dn[q], dot);
-                        dot = warp_sum(dot);
-                        const float xn = fmaf(x[u], g, dot);
-                        float* r = R + (int64_t)fdiv(ent[u], kdiv) * n;
-#pragma unroll
-                        for (int q = 0; q < NPL; ++q) {
-                            const int f = lane + 32 * q;
-                            if (f < n) r[f] = fmaf(-dn[q], xn, fmaf(dold[q], x[u], rv[u][q]));
-                        }
-                        if (lane == 0) val[ent[u]] = xn;
-                    }
+                for (int q = 0; q < NPL; ++q) {
+                    const int f = lane + 32 * q;
+                    if (f < n) __stcg(r + f, fmaf(-dn[q], xn, fmaf(dold[q], xo, r2[q])));
                 }
-                for (int p = lo + warp + SW_U * SW_WARPS; p < hi; p += SW_WARPS) {
-                    const int e2 = entries[p];
-                    const float xo = val[e2];
-                    float* r = R + (int64_t)fdiv(e2, kdiv) * n;
-                    float r2[NPL], dot = 0.f;
-#pragma unroll
-                    for (int q = 0; q < NPL; ++q) {
-                        const int f = lane + 32 * q;
-                        r2[q] = (f < n) ? r[f] : 0.f;
-                        dot = fmaf(r2[q], dn[q], dot);
-                    }
-                    dot = warp_sum(dot);
-                    const float xn = fmaf(xo, g, dot);
-#pragma unroll
-                    for (int q = 0; q < NPL; ++q) {
-                        const int f = lane + 32 * q;
-                        if (f < n) r[f] = fmaf(-dn[q], xn, fmaf(dold[q], xo, r2[q]));
-                    }
-                    __syncwarp();
-                    if (lane == 0) val[e2] = xn;
-                }
+                if (lane == 0) __stcg(a.val + e, xn);
             }
-            // rows/coefficients of this CTA's signals are re-read by other warps of THIS CTA only
-            __syncthreads();
-            lo = lo2; hi = hi2; lo2 = lo3; hi2 = hi3;
-#pragma unroll
-            for (int u = 0; u < SW_U; ++u) { ent[u] = ent2[u]; x[u] = x2n[u]; }
         }
+        // rows / coefficients of this CTA's signals are re-read by other warps of THIS CTA only
+        compute_sync<CW>();
+        // ---- rotate the pipeline
+        gP = g;
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) { dnP[q] = dn[q]; doldP[q] = dold[q]; dold[q] = doldN[q]; }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) rvC[u][q] = rvN[u][q];
+        setC = setN; rgC = rgN;
+        setN = setP; rgN = rgP;
     }
 }
 
 template <int NPL>
-int launch_sweep(float* R, float* Dt, float* val, const int32_t* rowptr, const int32_t* entries, const int32_t* bounds,
-                 int n, int K, int k, int n_cycles, int32_t* unused, float* partial, unsigned* flags,
-                 PeerComm pc, unsigned comm_seq0, int grid, cudaStream_t stream)
+int launch_sweep(const SweepArgs& args, int grid, cudaStream_t stream)
 {
-    FastDiv kdiv;
-    kdiv.s = 0;
-    while ((1 << kdiv.s) < k) ++kdiv.s;
-    kdiv.M = ((1ull << (32 + kdiv.s)) + (unsigned long long)k - 1) / (unsigned long long)k;
-    auto kern = ksvd_sweep_kernel<NPL>;
-    const int red_rows = std::max(SW_WARPS, (SW_WARPS * 32) / (n + 1));
-    size_t smem = sizeof(float) * (size_t)(2 * n + (n + 2) + red_rows * (n + 1));
+    const bool multi = args.pc.world > 1;
+    const void* kern = multi ? (const void*)ksvd_sweep_kernel<NPL, true> : (const void*)ksvd_sweep_kernel<NPL, false>;
+    const int threads = SW_THREADS;
+    const size_t smem = sizeof(float) * (size_t)(args.lda * (1 + 16));
     LYS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    LYS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SW_WARPS * 32, smem));
+    LYS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) { set_error("ksvd sweep kernel does not fit on an SM"); return LYS_ECUDA; }
-    void* args[] = {&R, &Dt, &val, &rowptr, &entries, &bounds, &n, &K, &k, &n_cycles, &unused, &partial, &flags, &pc, &comm_seq0, &kdiv};
-    LYS_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(SW_WARPS * 32), args, smem, stream));
+    SweepArgs a = args;
+    void* params[] = {&a};
+    LYS_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(threads), params, smem, stream));
     return LYS_OK;
 }
 
-int sweep_grid() { return std::min(sm_count(), 1024); }
+// one CTA per SM; the contribution counter of an accumulator word has 8 bits
+int sweep_grid() { return std::min(sm_count(), 255); }
+
+int sweep_lda(int n) { return (2 * n + 3 + 3) / 4 * 4; }
+// words between two accumulators: 32 bytes apart (their atomics then spread over more L2 slices) unless that makes
+// the array larger than 64 MB
+int sweep_acc_stride(int n, int K) { return ((size_t)K * sweep_lda(n) * 32 <= (64u << 20)) ? 4 : 1; }
 
 }  // namespace
 }  // namespace lys
 
 using namespace lys;
 
-extern "C" size_t lys_ksvd_sweep_workspace_bytes(int n, int K)
+namespace {
+struct SweepWs {
+    float* Dt; float* Dt_new; u64* acc; size_t acc_bytes; int32_t* bounds; double* fro; double* fx; void* frob_ws; uint8_t* link;
+    size_t total;
+};
+SweepWs carve(void* base, int n, int K, int64_t N, int k)
 {
-    const size_t G = 1024;     // upper bound on the grid
-    return align_up((size_t)n * K * 4, 256) + align_up(2 * G * (size_t)(n + 1) * 4, 256) + align_up(2 * G * 4, 256) +
-           align_up((size_t)K * (G + 1) * 4, 256) + 256;
+    SweepWs w;
+    unsigned char* p = reinterpret_cast<unsigned char*>(base);
+    auto take = [&](size_t bytes) { unsigned char* r = p; p += align_up(bytes, 256); return r; };
+    w.Dt = reinterpret_cast<float*>(take((size_t)n * K * 4));
+    w.Dt_new = reinterpret_cast<float*>(take((size_t)n * K * 4));
+    w.acc_bytes = (size_t)K * sweep_lda(n) * sweep_acc_stride(n, K) * sizeof(u64);
+    w.acc = reinterpret_cast<u64*>(take(w.acc_bytes));
+    w.bounds = reinterpret_cast<int32_t*>(take((size_t)K * 256 * 4));
+    w.fro = reinterpret_cast<double*>(take(4 * sizeof(double)));
+    w.fx = w.fro + 2;
+    w.frob_ws = take(sizeof(double) * 4096);
+    w.link = reinterpret_cast<uint8_t*>(take((size_t)std::max<int64_t>(N * k, 1)));
+    w.total = (size_t)(p - reinterpret_cast<unsigned char*>(base)) + 256;
+    return w;
+}
+}  // namespace
+
+extern "C" size_t lys_ksvd_sweep_workspace_bytes(int n, int K, int64_t N, int k)
+{
+    if (n < 1 || K < 1 || N < 0 || k < 1) return 0;
+    return carve(nullptr, n, K, N, k).total;
 }
 
 extern "C" int lys_approx_ksvd_sweep(float* R, float* D, int64_t ldd, const int32_t* idx, float* val,
@@ -382,42 +546,64 @@ extern "C" int lys_approx_ksvd_sweep(float* R, float* D, int64_t ldd, const int3
                                      void* stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
-    (void)idx;
-    LYS_CHECK_ARG(R && D && val && rowptr && entries && unused && workspace, "lys_approx_ksvd_sweep: null pointer");
-    LYS_CHECK_ARG(n >= 1 && n <= LYS_MAX_FEATURES && K >= 1 && K <= LYS_MAX_ATOMS && ldd >= K && k >= 1 && n_cycles >= 1 && N >= 0,
-                  "lys_approx_ksvd_sweep: bad shape");
-    if (workspace_bytes < lys_ksvd_sweep_workspace_bytes(n, K)) { set_error("lys_approx_ksvd_sweep: workspace too small"); return LYS_EWORKSPACE; }
+    LYS_CHECK_ARG(R && D && idx && val && rowptr && entries && unused && workspace, "lys_approx_ksvd_sweep: null pointer");
+    LYS_CHECK_ARG(n >= 1 && n <= LYS_MAX_FEATURES && K >= 1 && K <= LYS_MAX_ATOMS && ldd >= K && k >= 1 && k <= LYS_MAX_NONZERO &&
+                  n_cycles >= 1 && N >= 0, "lys_approx_ksvd_sweep: bad shape");
+    LYS_CHECK_ARG(N * (int64_t)k < (1ll << 31), "lys_approx_ksvd_sweep: N*k must fit int32");
+    LYS_CHECK_ARG((reinterpret_cast<uintptr_t>(R) & 15) == 0 && (reinterpret_cast<uintptr_t>(val) & 15) == 0,
+                  "lys_approx_ksvd_sweep: R and val must be 16-byte aligned");
+    if (workspace_bytes < lys_ksvd_sweep_workspace_bytes(n, K, N, k)) { set_error("lys_approx_ksvd_sweep: workspace too small"); return LYS_EWORKSPACE; }
     PeerComm pc{};
     pc.rank = 0; pc.world = 1;
-    unsigned seq0 = 0;
     CommHost* host = reinterpret_cast<CommHost*>(comm);
     if (host) {
         LYS_CHECK_ARG(host->connected, "lys_approx_ksvd_sweep: comm not connected (call lys_comm_connect)");
-        LYS_CHECK_ARG(n + 2 <= COMM_LD, "lys_approx_ksvd_sweep: n too large for the exchange slots");
         pc = host->dev;
     }
     const int grid = sweep_grid();
-    unsigned char* p = reinterpret_cast<unsigned char*>(workspace);
-    float* Dt = reinterpret_cast<float*>(p); p += align_up((size_t)n * K * 4, 256);
-    float* partial = reinterpret_cast<float*>(p); p += align_up(2 * (size_t)1024 * (n + 1) * 4, 256);
-    unsigned* flags = reinterpret_cast<unsigned*>(p); p += align_up(2 * (size_t)1024 * 4, 256);
-    int32_t* bounds = reinterpret_cast<int32_t*>(p);
-    LYS_CUDA(cudaMemsetAsync(flags, 0, 2 * (size_t)1024 * 4, stream));
+    const SweepWs w = carve(workspace, n, K, N, k);
     LYS_CUDA(cudaMemsetAsync(unused, 0, sizeof(int32_t) * (size_t)K, stream));
-    int rc = transpose(D, ldd, Dt, n, n, K, stream);
+    int rc = transpose(D, ldd, w.Dt, n, n, K, stream);
     if (rc) return rc;
     const int64_t S = std::max<int64_t>(1, (N + grid - 1) / grid);
     const int items = K * (grid + 1);
-    sweep_bounds_kernel<<<(items + 255) / 256, 256, 0, stream>>>(rowptr, entries, K, k, grid, S, bounds);
+    sweep_bounds_kernel<<<(items + 255) / 256, 256, 0, stream>>>(rowptr, entries, K, k, grid, S, w.bounds);
     LYS_LAUNCH_CHECK("sweep_bounds_kernel");
-    if (host) {
-        seq0 = host->epoch;
-        host->epoch += (unsigned)(n_cycles * K + 1);
+    if (N > 0) {
+        sweep_link_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(idx, val, N, k, w.link);
+        LYS_LAUNCH_CHECK("sweep_link_kernel");
     }
-    if (n <= 32) rc = launch_sweep<1>(R, Dt, val, rowptr, entries, bounds, n, K, k, n_cycles, unused, partial, flags, pc, seq0, grid, stream);
-    else if (n <= 64) rc = launch_sweep<2>(R, Dt, val, rowptr, entries, bounds, n, K, k, n_cycles, unused, partial, flags, pc, seq0, grid, stream);
-    else if (n <= 128) rc = launch_sweep<4>(R, Dt, val, rowptr, entries, bounds, n, K, k, n_cycles, unused, partial, flags, pc, seq0, grid, stream);
-    else rc = launch_sweep<8>(R, Dt, val, rowptr, entries, bounds, n, K, k, n_cycles, unused, partial, flags, pc, seq0, grid, stream);
-    if (rc) return rc;
-    return transpose(Dt, n, D, ldd, K, n, stream);
+
+    SweepArgs a{};
+    a.R = R; a.Dt = w.Dt; a.Dt_new = w.Dt_new; a.val = val;
+    a.entries = entries; a.link = w.link; a.bounds = w.bounds;
+    a.n = n; a.K = K; a.k = k; a.lda = sweep_lda(n); a.acc_stride = sweep_acc_stride(n, K);
+    a.unused = unused; a.acc = w.acc; a.fx = w.fx; a.pc = pc;
+    a.kdiv.s = 0;
+    while ((1 << a.kdiv.s) < k) ++a.kdiv.s;
+    a.kdiv.M = ((1ull << (32 + a.kdiv.s)) + (unsigned long long)k - 1) / (unsigned long long)k;
+
+    for (int cyc = 0; cyc < n_cycles; ++cyc) {
+        // fixed-point scale from the norms of the residual and of the coefficients as they are now
+        rc = lys_frobenius2(R, N * (int64_t)n, w.fro, w.frob_ws, sizeof(double) * 4096, stream);
+        if (rc) return rc;
+        rc = lys_frobenius2(val, N * (int64_t)k, w.fro + 1, w.frob_ws, sizeof(double) * 4096, stream);
+        if (rc) return rc;
+        unsigned gen = 0;
+        if (host) {
+            gen = host->generation;
+            host->generation += 1u + (unsigned)((K + COMM_WINDOW - 1) / COMM_WINDOW);
+        }
+        sweep_scale_kernel<<<1, 32, 0, stream>>>(w.fro, w.fx, pc, gen);
+        LYS_LAUNCH_CHECK("sweep_scale_kernel");
+        a.gen0 = gen + 1u;
+        LYS_CUDA(cudaMemsetAsync(w.acc, 0, w.acc_bytes, stream));
+        if (n <= 32) rc = launch_sweep<1>(a, grid, stream);
+        else if (n <= 64) rc = launch_sweep<2>(a, grid, stream);
+        else if (n <= 128) rc = launch_sweep<4>(a, grid, stream);
+        else rc = launch_sweep<8>(a, grid, stream);
+        if (rc) return rc;
+        LYS_CUDA(cudaMemcpyAsync(w.Dt, w.Dt_new, (size_t)n * K * 4, cudaMemcpyDeviceToDevice, stream));
+    }
+    return transpose(w.Dt, n, D, ldd, K, n, stream);
 }

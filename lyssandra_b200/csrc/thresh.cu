@@ -280,7 +280,7 @@ int launch_select(bool use_abs, const float* alpha, float scale, const int32_t* 
                   int K, int64_t C, int k, int32_t* idx, float* val, int32_t* nsel,
                   float* Z, int64_t zas, int64_t zss, cudaStream_t stream)
 {
-    if (k <= 32 && K <= 1024 && !getenv("LYS_SELECT_GENERIC")) {
+    if (k <= 32 && K <= 1024) {
         if (K <= 256) return launch_select_reg<8>(use_abs, alpha, scale, pidx, pval, pk, K, C, k, idx, val, nsel, Z, zas, zss, stream);
         if (K <= 512) return launch_select_reg<16>(use_abs, alpha, scale, pidx, pval, pk, K, C, k, idx, val, nsel, Z, zas, zss, stream);
         return launch_select_reg<32>(use_abs, alpha, scale, pidx, pval, pk, K, C, k, idx, val, nsel, Z, zas, zss, stream);

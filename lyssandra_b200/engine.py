@@ -277,7 +277,7 @@ def approx_ksvd_sweep(R, D, codes: SparseCodes, rowptr, entries, n_cycles=1, com
         raise ValueError("D must have contiguous rows")
     unused = torch.empty((K,), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        ws = workspace(dev, lib.lys_ksvd_sweep_workspace_bytes(n, K), tag="sweep")
+        ws = workspace(dev, lib.lys_ksvd_sweep_workspace_bytes(n, K, N, k), tag="sweep")
         nat.check(lib.lys_approx_ksvd_sweep(_ptr(R), _ptr(D), D.stride(0), _ptr(codes.idx), _ptr(codes.val),
                                             _ptr(rowptr), _ptr(entries), n, K, N, k, int(n_cycles),
                                             _ptr(unused), ctypes.c_void_p(comm or 0), _ptr(ws), ws.numel(),

@@ -115,3 +115,67 @@ int lys_oracle_batch_omp(const double* alpha, int alpha_signal_major, const doub
     }
     return status;
 }
+
+/* float64 restatement of the atom loop of approx_ksvd (lyssa/dict_learning/ksvd.py:105-124) on sparse codes, for
+ * sweeps too large for the dense NumPy restatement (oracle/lyssa_oracle.py::approx_ksvd, against which this function
+ * is validated in tests/test_oracle.py::test_c_sweep_matches_numpy_oracle).
+ *   R   (N, n) signal-major: the residual Y - D X of :103, updated in place (:123)
+ *   D   (n, K) C-order as in the reference, updated in place (:118-119)
+ *   idx/val (N, k): the non-zeros of the reference's dense X; users of atom c = entries with idx == c and
+ *       val != 0 (:111), visited in ascending signal order; val updated in place (:121)
+ *   unused (K): set to 1 for atoms without users (:112-115)
+ * Per atom, exactly the reference's sequence: Rk = R[:,users] + d x (:116); d = Rk x (:118);
+ * d /= ||d|| + eps (:119, utils/math.py:61-62); x = Rk^T d (:121); R[:,users] = Rk - d x (:123). */
+int lys_oracle_approx_ksvd_sweep(double* R, double* D, const int32_t* idx, double* val,
+                                 int64_t n_signals, int n, int64_t n_atoms, int k, int n_cycles, int32_t* unused)
+{
+    const int64_t E = n_signals * (int64_t)k;
+    int64_t* rowptr = (int64_t*)calloc((size_t)n_atoms + 1, sizeof(int64_t));
+    int64_t* ent = (int64_t*)malloc(sizeof(int64_t) * (size_t)(E > 0 ? E : 1));
+    int64_t* fill = (int64_t*)malloc(sizeof(int64_t) * (size_t)n_atoms);
+    double* Rk = NULL;
+    double* dnew = (double*)malloc(sizeof(double) * (size_t)n);
+    if (!rowptr || !ent || !fill || !dnew) return -1;
+    for (int64_t e = 0; e < E; ++e)
+        if (idx[e] >= 0 && idx[e] < n_atoms && val[e] != 0.0) rowptr[idx[e] + 1]++;
+    int64_t max_users = 0;
+    for (int64_t c = 0; c < n_atoms; ++c) {
+        if (rowptr[c + 1] > max_users) max_users = rowptr[c + 1];
+        rowptr[c + 1] += rowptr[c];
+        fill[c] = rowptr[c];
+    }
+    for (int64_t e = 0; e < E; ++e)
+        if (idx[e] >= 0 && idx[e] < n_atoms && val[e] != 0.0) ent[fill[idx[e]]++] = e;
+    Rk = (double*)malloc(sizeof(double) * (size_t)(max_users > 0 ? max_users : 1) * (size_t)n);
+    if (!Rk) return -1;
+    memset(unused, 0, sizeof(int32_t) * (size_t)n_atoms);
+    for (int cyc = 0; cyc < n_cycles; ++cyc) {
+        for (int64_t c = 0; c < n_atoms; ++c) {
+            const int64_t lo = rowptr[c], hi = rowptr[c + 1], m = hi - lo;
+            if (m == 0) { unused[c] = 1; continue; }                               /* :112-115 */
+            for (int f = 0; f < n; ++f) dnew[f] = 0.0;
+            for (int64_t u = 0; u < m; ++u) {                                       /* :116, :118 */
+                const int64_t e = ent[lo + u], i = e / k;
+                const double x = val[e];
+                for (int f = 0; f < n; ++f) {
+                    const double v = R[i * n + f] + D[(int64_t)f * n_atoms + c] * x;
+                    Rk[u * n + f] = v;
+                    dnew[f] += v * x;
+                }
+            }
+            double nrm = 0.0;
+            for (int f = 0; f < n; ++f) nrm += dnew[f] * dnew[f];
+            nrm = sqrt(nrm) + DBL_EPSILON;                                          /* :119 */
+            for (int f = 0; f < n; ++f) { dnew[f] /= nrm; D[(int64_t)f * n_atoms + c] = dnew[f]; }
+            for (int64_t u = 0; u < m; ++u) {                                       /* :121, :123 */
+                const int64_t e = ent[lo + u], i = e / k;
+                double x = 0.0;
+                for (int f = 0; f < n; ++f) x += Rk[u * n + f] * dnew[f];
+                val[e] = x;
+                for (int f = 0; f < n; ++f) R[i * n + f] = Rk[u * n + f] - dnew[f] * x;
+            }
+        }
+    }
+    free(rowptr); free(ent); free(fill); free(Rk); free(dnew);
+    return 0;
+}

@@ -30,6 +30,10 @@ def _load():
         _lib.lys_oracle_batch_omp.argtypes = [
             ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        _lib.lys_oracle_approx_ksvd_sweep.restype = ctypes.c_int
+        _lib.lys_oracle_approx_ksvd_sweep.argtypes = [
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+            ctypes.c_int64, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     return _lib
 
 
@@ -82,3 +86,28 @@ def densify(idx, val, n_atoms):
     ok = flat_i >= 0
     Z[flat_i[ok], rows[ok]] = val.reshape(-1)[ok]
     return Z
+
+
+def approx_ksvd_sparse(Y, D, idx, val, n_cycles=1):
+    """float64 approx_ksvd sweep (lyssa/dict_learning/ksvd.py:98-126) on sparse codes, in C: for sweeps too large
+    for the dense NumPy restatement.  Y (n, N), D (n, K), idx/val (N, k).  Returns (D', val', unused list, R')
+    with R' = Y - D' X' the (N, n) residual the sweep maintains (:123); inputs are not modified."""
+    lib = _load()
+    Y = np.asarray(Y, dtype=np.float64)
+    D = np.array(D, dtype=np.float64, order="C")
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    val = np.array(val, dtype=np.float64, order="C")
+    n, n_signals = Y.shape
+    n_atoms, k = D.shape[1], idx.shape[1]
+    R = np.ascontiguousarray(Y.T).copy()                       # :103  R = Y - D X, from the sparse codes
+    Dt = np.ascontiguousarray(D.T)
+    for s in range(k):
+        a = idx[:, s]
+        ok = a >= 0
+        R[ok] -= Dt[a[ok]] * val[ok, s][:, None]
+    unused = np.zeros(n_atoms, dtype=np.int32)
+    rc = lib.lys_oracle_approx_ksvd_sweep(R.ctypes.data, D.ctypes.data, idx.ctypes.data, val.ctypes.data,
+                                          n_signals, n, n_atoms, k, n_cycles, unused.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("lys_oracle_approx_ksvd_sweep failed: %d" % rc)
+    return D, val, np.nonzero(unused)[0].tolist(), R

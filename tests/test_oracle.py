@@ -118,6 +118,57 @@ def test_c_oracle_matches_numpy_oracle():
         assert np.allclose(gap, tr["gap"], rtol=1e-9, atol=1e-14)
 
 
+def test_c_sweep_matches_numpy_oracle():
+    """the C restatement of the atom loop (sparse codes, for full-size sweeps) against the dense NumPy restatement
+    of approx_ksvd (ksvd.py:98-126), including an atom nobody uses and a second cycle"""
+    n, K, N, k = 16, 24, 400, 4
+    rng = np.random.default_rng(31)
+    X = rng.standard_normal((n, N))
+    D = lo.norm_cols(rng.standard_normal((n, K)))
+    idx, val, nsel = co.batch_omp_sparse(X, D, k, threads=1)
+    idx = idx.copy()
+    val = val.copy()
+    kill = idx == 7                       # atom 7 loses all its users (:112-115)
+    idx[kill] = -1
+    val[kill] = 0.0
+    for cycles in (1, 2):
+        Z = co.densify(idx, val, K)
+        Dn, Zn, unused_n = lo.approx_ksvd(X.copy(), D.copy(), Z, n_cycles=cycles)
+        Dc, valc, unused_c, Rc = co.approx_ksvd_sparse(X, D, idx, val, n_cycles=cycles)
+        assert sorted(set(unused_n)) == unused_c == [7]
+        assert np.max(np.abs(Dn - Dc)) <= 1e-12
+        assert np.max(np.abs(Zn - co.densify(idx, valc, K))) <= 1e-11
+        assert np.max(np.abs((X - Dn @ Zn).T - Rc)) <= 1e-11
+
+
+def test_batch_omp_agrees_with_independent_solvers():
+    """SURVEY 8c KAT (7): the restated batch_omp against two solvers that share none of its recurrences — a plain
+    OMP that re-solves the normal equations from scratch at every step (the reference's own `_omp`,
+    sparse_coding.py:19-57: argmax |D^T r|, z = G[I,I]^-1 D_I^T x) and scikit-learn's orthogonal_mp_gram."""
+    X = lo.synthetic_patches(400, 64, seed=40).astype(float)
+    D = lo.norm_cols(lo.synthetic_dictionary(256, 64, seed=41).astype(float))     # unit norm in float64 (quirk Q1: batch_omp uses a literal 1)
+    k = 5
+    G, A = D.T @ D, D.T @ X
+    Z = lo.batch_omp(X, A, D, G, k)
+    Zp = np.zeros_like(Z)
+    for i in range(X.shape[1]):                                   # _omp, :19-57
+        x, sel, alpha = X[:, i], [], A[:, i].copy()
+        for _ in range(k):
+            j = int(np.argmax(np.abs(alpha)))
+            if j in sel:
+                break
+            sel.append(j)
+            z = np.linalg.solve(G[np.ix_(sel, sel)], A[sel, i])
+            alpha = D.T @ (x - D[:, sel] @ z)
+        Zp[sel, i] = z
+    assert np.array_equal(Z != 0, Zp != 0)
+    assert np.max(np.abs(Z - Zp)) <= 1e-12
+    sk = pytest.importorskip("sklearn.linear_model")
+    Zs = sk.orthogonal_mp_gram(G, A, n_nonzero_coefs=k)
+    assert np.array_equal(Z != 0, Zs != 0)
+    assert np.max(np.abs(Z - Zs)) <= 1e-12
+
+
 def test_batches_and_quirks():
     assert [len(r) for r in lo.gen_even_batches(250, 100)] == [2] * 99 + [52]
     assert [len(r) for r in lo.gen_even_batches(50, 100)] == [0] * 99 + [50]      # quirk Q8
