@@ -177,63 +177,116 @@ def tensor_info(peaks, n, K, k, patches, kernel_ms):
 def ksvd_iteration_ms(dev, rank, world, iters=3):
     """K-SVD iteration time at BASELINE cfg3 (2M 8x8 patches in total, K=1024, k=10), patch-sharded
     over the ranks: Batch-OMP encode -> residual -> users-of-atom CSR -> sweep (per-atom all-reduce
-    inside the kernel over peer-mapped buffers when world > 1) -> error (+ scalar all-reduce).
-    Returns (median ms per iteration on this rank, stage split)."""
+    inside the kernel over peer-mapped mailboxes when world > 1) -> error (+ scalar all-reduce).
+    Every timed iteration starts from the same D (a rate, not cfg3's 20-iteration trajectory).
+    Returns (median ms per iteration on this rank, stage split, parity dict or None)."""
     import torch
+    import torch.distributed as dist
     from lyssandra_b200 import engine
     from lyssandra_b200.distributed import DistContext, PeerExchange
     from lyssandra_b200.sparse_coding import sparse_encoder
     from oracle import lyssa_oracle as lo
     n, K, k, N = 64, 1024, 10, 2000000 // world
     X = torch.from_numpy(np.ascontiguousarray(lo.synthetic_patches(N, n, seed=2000 + rank).T)).to(dev).t()
-    D = torch.from_numpy(lo.synthetic_dictionary(K, n, seed=1)).to(dev)
+    D0 = torch.from_numpy(lo.synthetic_dictionary(K, n, seed=1)).to(dev)
     ctx = DistContext.from_env_or_group()
     ex = PeerExchange(ctx)
     enc = sparse_encoder("bomp", {"n_nonzero_coefs": k}, verbose=False)
+
+    def iteration(Xs, D, comm, timed=True):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        ev[0].record(); codes = enc.encode_sparse(Xs, D)
+        ev[1].record(); R, _ = engine.residual(Xs, D, codes, want_residual=True, want_error=False)
+        ev[2].record(); rowptr, entries = engine.build_atom_csr(codes)
+        ev[3].record(); engine.approx_ksvd_sweep(R, D, codes, rowptr, entries, n_cycles=1, comm=comm)
+        ev[4].record(); err = engine.frobenius2(R)     # R is kept current by the sweep
+        if comm is not None:
+            ctx.allreduce_sum_(err)
+        ev[5].record(); torch.cuda.synchronize(dev)
+        return ev, err
+
     totals, stages = [], []
     for it in range(iters + 1):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        D = D0.clone()
         torch.cuda.synchronize(dev); ctx.barrier()
-        ev[0].record(); codes = enc.encode_sparse(X, D)
-        ev[1].record(); R, _ = engine.residual(X, D, codes, want_residual=True, want_error=False)
-        ev[2].record(); rowptr, entries = engine.build_atom_csr(codes)
-        ev[3].record(); engine.approx_ksvd_sweep(R, D, codes, rowptr, entries, n_cycles=1, comm=ex.handle)
-        ev[4].record(); err = engine.frobenius2(R); ctx.allreduce_sum_(err)     # R is kept current by the sweep
-        ev[5].record(); torch.cuda.synchronize(dev)
+        ev, _ = iteration(X, D, ex.handle)
         if it > 0:
             totals.append(ev[0].elapsed_time(ev[5]))
             stages.append([ev[i].elapsed_time(ev[i + 1]) for i in range(5)])
+
+    # ---- parity of the sharded sweep against ONE GPU on the same signals (a 262144-patch slice: the first
+    # 262144/world patches of every shard, gathered on rank 0 in rank order)
+    parity = None
+    if world > 1:
+        m = 262144 // world
+        Xs = X[:, :m]
+        Dsh = D0.clone()
+        torch.cuda.synchronize(dev); ctx.barrier()
+        _, err_sh = iteration(Xs, Dsh, ex.handle)
+        mine = Xs.t().contiguous()                                      # (m, n)
+        allX = torch.empty((world * m, n), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(allX, mine)
+        allD = torch.empty((world,) + tuple(Dsh.shape), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(allD, Dsh.contiguous())
+        if rank == 0:
+            D1 = D0.clone()
+            _, err_1 = iteration(allX.t(), D1, None)
+            parity = {"signals": world * m,
+                      "sweep_max_dD_vs_1gpu": float((D1 - Dsh).abs().max()),
+                      "D_identical_across_ranks": bool(all(torch.equal(allD[r], allD[0]) for r in range(world))),
+                      "objective_rel": abs(float(err_sh.item()) - float(err_1.item())) / float(err_1.item())}
+        torch.cuda.synchronize(dev); ctx.barrier()
     ex.close()
     med = [float(np.median([s[i] for s in stages])) for i in range(5)]
-    return float(np.median(totals)), dict(zip(["encode", "residual", "csr", "sweep", "error"], med))
+    return float(np.median(totals)), dict(zip(["encode", "residual", "csr", "sweep", "error"], med)), parity
 
 
-def scspm_images_per_s(dev, n_imgs=128, size=256, reps=3):
-    """ScSPM pipeline in the shape of BASELINE cfg5, scaled to one batch: synthetic 256x256 images -> dense SIFT
-    (16x16 patches, grid step 6: 41x41 descriptors per image) -> Batch-OMP (D 128x1024, k=5) -> 3-level max-|z|
-    pooling + l2 normalisation.  Images are resident on the device; returns (images/s, descriptors per image)."""
+def _scspm_block(b, chunk, size):
+    """synthetic smooth-noise images of block b (any rank can regenerate any block)"""
+    rng = np.random.default_rng(5000 + b)
+    base = rng.random((chunk, size + 8, size + 8), dtype=np.float32)
+    return (base[:, :-8, :-8] + base[:, 4:-4, 4:-4] + base[:, 8:, 8:]) * (255.0 / 3.0)
+
+
+def scspm_images_per_s(dev, rank, world, n_total=10000, size=256, chunk=250):
+    """ScSPM pipeline of BASELINE cfg5: 10k synthetic 256x256 images, sharded by image over the ranks (no collective)
+    -> dense SIFT (16x16 patches, grid step 6: 41x41 descriptors per image) -> Batch-OMP (D 128x1024, k=5) -> 3-level
+    max-|z| pooling + l2 normalisation.  Images are resident on the device; blocks of `chunk` images per call.
+    Returns (ms for this rank's shard, parity dict or None)."""
     import torch
+    import torch.distributed as dist
     from lyssandra_b200.sparse_coding import sparse_encoder
     from lyssandra_b200.feature_extract import sc_spm_extractor, dsift_extractor, sc_max_pooling, l2_normalizer
+    from lyssandra_b200.utils import shard_bounds
     from oracle import lyssa_oracle as lo
-    rng = np.random.default_rng(5)
-    base = rng.random((n_imgs, size + 8, size + 8), dtype=np.float32)
-    imgs_h = (base[:, :-8, :-8] + base[:, 4:-4, 4:-4] + base[:, 8:, 8:]) * (255.0 / 3.0)
-    imgs = [torch.from_numpy(np.ascontiguousarray(im)).to(dev) for im in imgs_h]
+    n_blocks = n_total // chunk
+    b_lo, b_hi = shard_bounds(n_blocks, world, rank)
+    blocks = [[torch.from_numpy(np.ascontiguousarray(im)).to(dev) for im in _scspm_block(b, chunk, size)] for b in range(b_lo, b_hi)]
     D = torch.from_numpy(lo.synthetic_dictionary(1024, 128, seed=9)).to(dev)
     enc = sparse_encoder("bomp", {"n_nonzero_coefs": 5}, verbose=False)
     ex = sc_spm_extractor(feature_extractor=dsift_extractor(step_size=6, patch_size=16), levels=(1, 2, 4), sparse_coder=enc,
                           pooling_operator=sc_max_pooling(), normalizer=l2_normalizer())
-    F = ex.encode(imgs, D)
+    F = [ex.encode(blocks[0], D)]
     torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(reps):
-        F = ex.encode(imgs, D)
+    F = [ex.encode(imgs, D) for imgs in blocks]
     e1.record()
     torch.cuda.synchronize(dev)
-    assert tuple(F.shape) == (21 * 1024, n_imgs) and bool(torch.isfinite(F).all())
-    return n_imgs * reps / (e0.elapsed_time(e1) / 1e3), 41 * 41
+    ms = e0.elapsed_time(e1)
+    assert tuple(F[0].shape) == (21 * 1024, chunk) and all(bool(torch.isfinite(f).all()) for f in F)
+    parity = None
+    if world > 1:
+        # the first block of the LAST rank's shard, recomputed by rank 0 alone from the same seed
+        last_lo, _ = shard_bounds(n_blocks, world, world - 1)
+        ref = F[0].contiguous() if rank == world - 1 else torch.empty((21 * 1024, chunk), dtype=torch.float32, device=dev)
+        dist.broadcast(ref, src=world - 1)
+        if rank == 0:
+            mine = ex.encode([torch.from_numpy(np.ascontiguousarray(im)).to(dev) for im in _scspm_block(last_lo, chunk, size)], D)
+            parity = {"images": chunk, "max_dF_vs_1gpu": float((mine - ref).abs().max()), "identical": bool(torch.equal(mine, ref))}
+    return ms, parity
 
 
 def odl_minibatch_ms(dev, n=128, K=2048, k=5, b=4096):
@@ -418,17 +471,17 @@ def run_own(args):
 
     del Xpin, Zpin, ipin, vpin, spin, Zt
     torch.cuda.empty_cache()
-    ksvd_ms, ksvd_stages, ksvd_note = None, None, None
+    ksvd_ms, ksvd_stages, ksvd_note, ksvd_parity = None, None, None, None
     if not args.no_extras:
         try:
-            ksvd_ms, ksvd_stages = ksvd_iteration_ms(dev, rank, world)
+            ksvd_ms, ksvd_stages, ksvd_parity = ksvd_iteration_ms(dev, rank, world)
         except Exception as exc:          # secondary metric: reported, never fatal for the headline line
             ksvd_ms, ksvd_note = None, "failed: %r" % (exc,)
 
-    spm_rate, spm_note = None, None
-    if not args.no_extras and rank == 0:
+    spm_ms, spm_note, spm_parity = -1.0, None, None
+    if not args.no_extras:
         try:
-            spm_rate, _ = scspm_images_per_s(dev)
+            spm_ms, spm_parity = scspm_images_per_s(dev, rank, world)
         except Exception as exc:
             spm_note = "failed: %r" % (exc,)
 
@@ -446,11 +499,11 @@ def run_own(args):
         except Exception as exc:
             sib_note = "failed: %r" % (exc,)
 
-    t = torch.tensor([ms, e2e_s * 1e3 / e2e_steps, e2e_sparse_s * 1e3 / e2e_steps, ksvd_ms if ksvd_ms is not None else -1.0],
+    t = torch.tensor([ms, e2e_s * 1e3 / e2e_steps, e2e_sparse_s * 1e3 / e2e_steps, ksvd_ms if ksvd_ms is not None else -1.0, spm_ms],
                      dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms, e2e_sparse_ms, ksvd_ms_max = [float(v) for v in t.tolist()]
+    ms_max, e2e_ms, e2e_sparse_ms, ksvd_ms_max, spm_ms_max = [float(v) for v in t.tolist()]
 
     if rank == 0:
         peaks = {}
@@ -490,10 +543,13 @@ def run_own(args):
             "cpu_baseline": cpu_base,
             "extras": {"ksvd_iteration": {"workload": "approx K-SVD iteration, 2M 8x8 patches total (patch-sharded x%d), K=1024, k=10, n_cycles=1" % world,
                                           "ms_per_iter": ksvd_ms_max if ksvd_ms_max >= 0 else None, "stages_ms_rank0": ksvd_stages,
-                                          "collective": "none" if world == 1 else "per-atom (n+2)-float all-reduce inside the sweep kernel over peer-mapped NVLink buffers; scalar NCCL all-reduce of the error",
+                                          "collective": "none" if world == 1 else "per-atom all-reduce of 2n+3 fixed-point words inside the sweep kernel over peer-mapped NVLink mailboxes; scalar NCCL all-reduce of the error",
+                                          "timing": "median of 3 iterations, each from the same initial D (a per-iteration rate, not cfg3's 20-iteration trajectory)",
+                                          "parity_vs_1gpu": ksvd_parity,
                                           "note": ksvd_note},
-                       "scspm_pipeline": {"workload": "128 synthetic 256x256 images (rank 0 only) -> dense SIFT 16x16 / step 6 (1681 descriptors per image) -> Batch-OMP D 128x1024 k=5 -> 3-level max-|z| pooling + l2, images resident on the device",
-                                          "images_per_s": spm_rate, "note": spm_note},
+                       "scspm_pipeline": {"workload": "BASELINE cfg5: 10000 synthetic 256x256 images sharded by image over %d GPU(s), no collective -> dense SIFT 16x16 / step 6 (1681 descriptors per image) -> Batch-OMP D 128x1024 k=5 -> 3-level max-|z| pooling + l2, images resident on the device, 250 images per call" % world,
+                                          "images_per_s": (10000.0 / (spm_ms_max / 1e3)) if spm_ms_max > 0 else None, "ms_total_max_over_ranks": spm_ms_max if spm_ms_max > 0 else None,
+                                          "parity_vs_1gpu": spm_parity, "note": spm_note},
                        "odl_minibatch": {"workload": "ODL minibatch (rank 0 only): 4096 SIFT-like 128-d descriptors, D 128x2048, k=5, beta=0.9: encode -> A,B statistics -> dictionary update",
                                          "ms_per_minibatch": odl_ms, "stages_ms": odl_stages, "note": odl_note},
                        "sibling_coders": {"workload": "'thresh' / 'iht' coders, 1M synthetic patches (rank 0 only), D 64x1024, k=5, eta=0.2, sparse codes out unless noted",

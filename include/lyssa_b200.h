@@ -46,6 +46,7 @@ extern "C" {
 #define LYS_EUNSUPPORTED -4   /* shape outside what the kernels are built for */
 
 #define LYS_MAX_NONZERO   32  /* k  <= 32 */
+#define LYS_OMP_MAX_NONZERO 64  /* atoms per signal of the `omp` coder */
 #define LYS_MAX_ATOMS   4096  /* K  <= 4096 */
 #define LYS_MAX_FEATURES 256  /* n  <= 256 */
 
@@ -92,6 +93,41 @@ LYS_API int lys_bomp_encode(const float* X, int64_t x_feat_stride, int64_t x_sig
                     int32_t* idx, float* val, int32_t* nsel,
                     float* Z, int64_t z_atom_stride, int64_t z_sig_stride,
                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same call with option flags.  On the fused tcgen05 path (n <= 64, K in {256,...,1024}, k <= 10) the correlations
+ * D^T r of every greedy step are three fp16 split products (fp32-faithful values).  LYS_BOMP_SCREEN computes ONE fp16
+ * product that only ranks: a winner is accepted when a measured error bound certifies it (96.6 % of the decisions at
+ * cfg2) and is otherwise recomputed exactly in fp32 by the warp (bomp_fused.cu), so the selection is the exact
+ * first-maximum argmax of :322 either way and both modes return the same codes.  A third of the tensor work — but
+ * measured SLOWER (2.21 vs 1.41 ms per 1M patches): the kernel is bound by the per-signal
+ * scan/update chain, not by the tensor pipe, and the exact recomputations lengthen that chain.  Kept as an option
+ * for A/B measurements; other shapes ignore the flag. */
+#define LYS_BOMP_SCREEN 2
+LYS_API int lys_bomp_encode_ex(const float* X, int64_t x_feat_stride, int64_t x_sig_stride,
+                       const float* D, int64_t ldd, const float* G,
+                       int n, int K, int64_t N, int k,
+                       int32_t* idx, float* val, int32_t* nsel,
+                       float* Z, int64_t z_atom_stride, int64_t z_sig_stride,
+                       void* workspace, size_t workspace_bytes, int flags, void* stream);
+
+/* ---- the reference's plain OMP coder on the same Gram / correlation front end ------------------------------
+ * replaces algorithm 'omp' (the reference's DEFAULT algorithm; lyssa/sparse_coding.py:618-625 dispatch, :19-66 omp/_omp):
+ * per signal, while the continue criterion holds: first-maximum argmax of |D^T r| (:40), stop if already selected
+ * (:41-42), z = inv(G[I,I]) (D^T x)[I] with the TRUE Gram (no unit-norm assumption, unlike batch_omp; :45-53),
+ * r = x - D_I z (:54).  Criterion (:27-34): `strict` != 0 — the n_nonzero_coefs form — continue while fewer than
+ * k_max atoms are selected and ||r|| > tol (the reference forces tol = 1e-10 there); `strict` == 0 — the
+ * tolerance-only form — continue while ||r|| >= tol, up to k_max <= LYS_OMP_MAX_NONZERO atoms; *truncated (device
+ * int32, may be NULL, must be zeroed by the caller) counts the signals that still satisfied the criterion at k_max
+ * atoms (the reference would have gone on).  ||r|| comes from ||x||^2 - y.y in float32, i.e. it is resolved to about
+ * 3e-4 ||x||; a singular G[I,I] (the reference's LinAlgError, :48-51) stops the signal with the previous z.
+ * idx/val are (N, k_max); Z as in lys_bomp_encode. */
+LYS_API size_t lys_omp_workspace_bytes(int n, int K, int64_t N, int k_max);
+LYS_API int lys_omp_encode(const float* X, int64_t x_feat_stride, int64_t x_sig_stride,
+                   const float* D, int64_t ldd, const float* G,
+                   int n, int K, int64_t N, int k_max, float tol, int strict,
+                   int32_t* idx, float* val, int32_t* nsel,
+                   float* Z, int64_t z_atom_stride, int64_t z_sig_stride, int32_t* truncated,
+                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* The correlation GEMM alone (test/bring-up hook): alpha (C,K) row-major = X^T D.
  * impl: 0 = what lys_bomp_encode uses, 1 = fp32 SIMT, 2 = tcgen05 bf16x3 (n = 64 or 128, K % 256 == 0). */

@@ -39,12 +39,14 @@ def _fingerprint():
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False, bringup: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, bringup: bool = False, variant: str = "", defines=()) -> str:
     """Product library, or with ``bringup`` a separate liblyssa_b200_bringup.so compiled with -DLYS_BRINGUP
-    (in-kernel phase timers and their debug hooks; load it through LYSSA_B200_LIB — scripts only)."""
-    if bringup:
-        return _build_to(os.path.join(_PKG, "liblyssa_b200_bringup.so"), os.path.join(_PKG, "build_bringup"),
-                         ["-DLYS_BRINGUP"], verbose)
+    (in-kernel phase timers and their debug hooks), or with ``variant``/``defines`` an experiment build
+    liblyssa_b200_<variant>.so; the non-product builds are loaded through LYSSA_B200_LIB by scripts only."""
+    if bringup or variant:
+        name = variant or "bringup"
+        flags = list(defines) + (["-DLYS_BRINGUP"] if bringup else [])
+        return _build_to(os.path.join(_PKG, "liblyssa_b200_%s.so" % name), os.path.join(_PKG, "build_%s" % name), flags, verbose)
     fp = _fingerprint()
     if not force and os.path.isfile(LIB_PATH) and os.path.isfile(_STAMP):
         with open(_STAMP) as fh:

@@ -12,6 +12,8 @@ c_int, c_i64, c_f, c_vp, c_sz = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ct
 
 LYS_OK, LYS_EINVAL, LYS_ECUDA, LYS_EWORKSPACE, LYS_EUNSUPPORTED = 0, -1, -2, -3, -4
 MAX_NONZERO, MAX_ATOMS, MAX_FEATURES = 32, 4096, 256
+BOMP_SCREEN = 2
+OMP_MAX_NONZERO = 64
 COMM_HANDLE_BYTES = 64
 
 # name -> (restype, argtypes); mirrors include/lyssa_b200.h declaration by declaration
@@ -26,6 +28,11 @@ SIGNATURES = {
     "lys_bomp_workspace_bytes": (c_sz, [c_int, c_int, c_i64, c_int]),
     "lys_bomp_encode": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_i64, c_int,
                                 c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_sz, c_vp]),
+    "lys_bomp_encode_ex": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_i64, c_int,
+                                   c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_sz, c_int, c_vp]),
+    "lys_omp_workspace_bytes": (c_sz, [c_int, c_int, c_i64, c_int]),
+    "lys_omp_encode": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_i64, c_int, c_f, c_int,
+                               c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "lys_thresh_workspace_bytes": (c_sz, [c_int, c_int, c_i64]),
     "lys_thresh_encode": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_i64, c_int,
                                   c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_sz, c_vp]),

@@ -14,6 +14,11 @@ int bomp_greedy_generic(const float* alpha, const float* G, int K, int64_t C, in
                         int32_t* idx, float* val, int32_t* nsel,
                         float* Z, int64_t zas, int64_t zss, cudaStream_t stream);
 
+int omp_greedy_generic(const float* alpha, const float* G, int K, int64_t C, int k, const float* xnorm2, float tol, int strict,
+                       int32_t* idx, float* val, int32_t* nsel, float* Z, int64_t zas, int64_t zss, int32_t* truncated,
+                       cudaStream_t stream);
+int col_norm2(const float* X, int64_t xfs, int64_t xss, int n, int64_t C, float* out, cudaStream_t stream);
+
 bool bomp_fast_supported(int K, int k, int64_t zas, bool has_Z, const float* Z, int64_t zss);
 int bomp_greedy_fast(const float* alpha, const float* G, int K, int64_t C, int k,
                      int32_t* idx, float* val, int32_t* nsel, float* Z, int64_t zss, cudaStream_t stream);
@@ -29,7 +34,7 @@ int bomp_encode_fused(const float* X, int64_t xfs, int64_t xss, const float* D, 
                       const float* G, int n, int K, int64_t N, int k,
                       int32_t* idx, float* val, int32_t* nsel,
                       float* Z, int64_t zas, int64_t zss,
-                      void* workspace, size_t workspace_bytes, cudaStream_t stream);
+                      void* workspace, size_t workspace_bytes, int screen, cudaStream_t stream);
 size_t bomp_fused_workspace_bytes(int n, int K, int64_t N, int k);
 int bomp_fused_launch_count(int n, int K, int64_t N, int k);
 
@@ -120,7 +125,18 @@ extern "C" int lys_bomp_encode(const float* X, int64_t xfs, int64_t xss,
                                float* Z, int64_t zas, int64_t zss,
                                void* workspace, size_t workspace_bytes, void* stream_)
 {
+    return lys_bomp_encode_ex(X, xfs, xss, D, ldd, G, n, K, N, k, idx, val, nsel, Z, zas, zss, workspace, workspace_bytes, 0, stream_);
+}
+
+extern "C" int lys_bomp_encode_ex(const float* X, int64_t xfs, int64_t xss,
+                                  const float* D, int64_t ldd, const float* G,
+                                  int n, int K, int64_t N, int k,
+                                  int32_t* idx, float* val, int32_t* nsel,
+                                  float* Z, int64_t zas, int64_t zss,
+                                  void* workspace, size_t workspace_bytes, int flags, void* stream_)
+{
     cudaStream_t stream = (cudaStream_t)stream_;
+    LYS_CHECK_ARG((flags & ~LYS_BOMP_SCREEN) == 0, "lys_bomp_encode_ex: unknown flags 0x%x", flags);
     LYS_CHECK_ARG(n >= 1 && n <= LYS_MAX_FEATURES, "lys_bomp_encode: n=%d out of range [1,%d]", n, LYS_MAX_FEATURES);
     LYS_CHECK_ARG(K >= 1 && K <= LYS_MAX_ATOMS, "lys_bomp_encode: K=%d out of range [1,%d]", K, LYS_MAX_ATOMS);
     LYS_CHECK_ARG(k >= 1 && k <= LYS_MAX_NONZERO && k <= K,
@@ -138,7 +154,7 @@ extern "C" int lys_bomp_encode(const float* X, int64_t xfs, int64_t xss,
     }
 
     int rc = bomp_encode_fused(X, xfs, xss, D, ldd, G, n, K, N, k, idx, val, nsel, Z, zas, zss,
-                               workspace, workspace_bytes, stream);
+                               workspace, workspace_bytes, (flags & LYS_BOMP_SCREEN) != 0, stream);
     if (rc != LYS_EUNSUPPORTED) return rc;
 
     // generic path: per chunk, Alpha = X_chunk^T D (fp32 GEMM) then one warp per signal
@@ -166,6 +182,56 @@ extern "C" int lys_bomp_encode(const float* X, int64_t xfs, int64_t xss,
                                      nsel ? nsel + s0 : nullptr,
                                      Z ? Z + s0 * zss : nullptr, zas, zss, stream);
         if (prof) cudaEventRecord(stop_ev, stream);
+        if (rc) return rc;
+    }
+    return LYS_OK;
+}
+
+extern "C" size_t lys_omp_workspace_bytes(int n, int K, int64_t N, int k_max)
+{
+    if (n < 1 || K < 1 || N < 0 || k_max < 1) return 0;
+    const int64_t chunk = generic_chunk(K, N);
+    return align_up((size_t)chunk * (size_t)K * sizeof(float), 256) + align_up(corr_gemm_tc_planes_bytes(n, K), 256) +
+           align_up((size_t)chunk * sizeof(float), 256) + 256;
+}
+
+extern "C" int lys_omp_encode(const float* X, int64_t xfs, int64_t xss, const float* D, int64_t ldd, const float* G,
+                              int n, int K, int64_t N, int k, float tol, int strict,
+                              int32_t* idx, float* val, int32_t* nsel,
+                              float* Z, int64_t zas, int64_t zss, int32_t* truncated,
+                              void* workspace, size_t workspace_bytes, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LYS_CHECK_ARG(n >= 1 && n <= LYS_MAX_FEATURES, "lys_omp_encode: n=%d out of range [1,%d]", n, LYS_MAX_FEATURES);
+    LYS_CHECK_ARG(K >= 1 && K <= LYS_MAX_ATOMS, "lys_omp_encode: K=%d out of range [1,%d]", K, LYS_MAX_ATOMS);
+    LYS_CHECK_ARG(k >= 1 && k <= LYS_OMP_MAX_NONZERO && k <= K,
+                  "lys_omp_encode: k_max=%d must be in [1, min(K=%d, %d)]", k, K, LYS_OMP_MAX_NONZERO);
+    LYS_CHECK_ARG(tol >= 0.f, "lys_omp_encode: tol < 0");
+    LYS_CHECK_ARG(N >= 0, "lys_omp_encode: N < 0");
+    if (N == 0) return LYS_OK;
+    LYS_CHECK_ARG(X && D && G && idx && val && workspace, "lys_omp_encode: null pointer");
+    LYS_CHECK_ARG(ldd >= K, "lys_omp_encode: ldd < K");
+    LYS_CHECK_ARG(!Z || (zas >= 1 && zss >= 1), "lys_omp_encode: bad Z strides");
+    if (workspace_bytes < lys_omp_workspace_bytes(n, K, N, k)) {
+        set_error("lys_omp_encode: workspace %zu B < required %zu B", workspace_bytes, lys_omp_workspace_bytes(n, K, N, k));
+        return LYS_EWORKSPACE;
+    }
+    const int64_t chunk = generic_chunk(K, N);
+    unsigned char* p = reinterpret_cast<unsigned char*>(workspace);
+    float* alpha = reinterpret_cast<float*>(p); p += align_up((size_t)chunk * (size_t)K * sizeof(float), 256);
+    void* planes = p; p += align_up(corr_gemm_tc_planes_bytes(n, K), 256);
+    float* xn2 = reinterpret_cast<float*>(p);
+    const bool use_tc = corr_gemm_tc_supported(n, K);
+    int rc = LYS_OK;
+    if (use_tc && (rc = corr_gemm_tc_prepare(D, ldd, n, K, planes, stream))) return rc;
+    for (int64_t s0 = 0; s0 < N; s0 += chunk) {
+        const int64_t C = std::min(chunk, N - s0);
+        if (use_tc) rc = corr_gemm_tc(X + s0 * xss, xfs, xss, planes, n, K, C, alpha, stream);
+        else rc = sgemm_strided(X + s0 * xss, xss, xfs, D, ldd, 1, alpha, K, 1, C, K, n, stream);
+        if (rc) return rc;
+        if ((rc = col_norm2(X + s0 * xss, xfs, xss, n, C, xn2, stream))) return rc;
+        rc = omp_greedy_generic(alpha, G, K, C, k, xn2, tol, strict, idx + s0 * k, val + s0 * k, nsel ? nsel + s0 : nullptr,
+                                Z ? Z + s0 * zss : nullptr, zas, zss, truncated, stream);
         if (rc) return rc;
     }
     return LYS_OK;

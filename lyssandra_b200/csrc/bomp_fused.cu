@@ -14,19 +14,21 @@
 //              L <- [L; w, sqrt(pivot)]               (:337,:348-349)
 //              z = L^-T L^-1 alpha0[I]                (:353-354; alpha0[I] = D_I^T x in fp32)
 //              r_{j+1} = x - D_I z
-// Precision, default ("screen") mode: the tensor cores only RANK.  Every operand is scaled by a power of two and
-// rounded to fp16 (hi = rn16(v)); ONE product hi*hi per k-step is accumulated in fp32 in TMEM.  Its distance to the
-// exact correlation is bounded, per signal and step, by  E = ||r - r~|| max_c||d~_c|| + ||r|| max_c||d_c - d~_c||
-// (+ the accumulation error), all four norms measured, none assumed.  The scan keeps the maximum M, the best value
-// outside the winning 32-column piece and the piece maxima; if nothing else comes within 2E of M the winner is
-// the exact argmax (certified: ~97 % of the decisions at cfg2).  Otherwise the warp recomputes, cooperatively and in
-// fp32 from the atom-major fp32 dictionary, every column of every piece whose maximum is within 2E of M and takes the
-// first maximum of those exact values: the selection is exact in all cases, the tensor work is a third of the
-// split-product scheme.  Everything after the argmax (Cholesky row, coefficients, residual) is fp32 from the fp32
-// dictionary in both modes, so the two modes return identical codes.
-// "split3" mode (LYS_BOMP_SPLIT3, kept for A/B checks and used by the 'thresh' coder, which needs k ranked values):
-// operands split exactly into two fp16 planes (hi = rn16(v), lo = rn16(v - hi), 22+ mantissa bits);
-// hi*hi + lo*hi + hi*lo accumulated in fp32 in TMEM (3 MMAs per k-step; the dropped lo*lo term is 2^-22 relative).
+// Precision (default): every fp32 operand is scaled by a power of two and split exactly into two fp16
+// planes (hi = rn16(v), lo = rn16(v - hi), 22+ mantissa bits); hi*hi + lo*hi + hi*lo are
+// accumulated in fp32 in TMEM (3 MMAs per k-step; the dropped lo*lo term is 2^-22 relative).
+// "Screen" mode (LYS_BOMP_SCREEN, A/B option): the tensor cores only RANK.  ONE product hi*hi per k-step; its
+// distance to the exact correlation is bounded, per signal and step, by
+//     E = ||r - r~|| max_c||d~_c|| + ||r|| max_c||d_c - d~_c||  (+ the accumulation error),
+// all four norms measured, none assumed.  The scan keeps the maximum M, the best value outside the winning
+// 32-column piece and the piece maxima; if nothing else comes within 2E of M the winner is the exact argmax
+// (certified: 96.6 % of the decisions at cfg2).  Otherwise the warp recomputes, cooperatively and in fp32 from the
+// atom-major fp32 dictionary, every column of every piece whose maximum is within 2E of M (2.0 pieces on average)
+// and takes the first maximum of those exact values.  Everything after the argmax is the same fp32 code in both
+// modes, so they return identical codes (tests/test_gpu_encode.py).  Measured: a third of the tensor work but
+// 2.21 ms instead of 1.41 ms per 1M patches — the phase timers of the bring-up build show the kernel bound by the
+// per-signal chain (scan 5.5 k, update 6 k cycles per warp and step), not by the tensor pipe; the exact
+// recomputations add 6.5 k cycles of L2 round trips to that chain.
 //
 // Decomposition: a tile is 128 signals (TMEM lanes = MMA M); atoms are processed in chunks of
 // 256 (MMA N = one 256-column accumulator stage; two stages).  The fp16 planes of the whole
@@ -46,8 +48,8 @@
 // it waits on (the two slots alternate on the two stages; a parity wait must never be two
 // phases behind).
 //
-// Roofline: HBM, 4n + 4K bytes per signal (x in, dense Z row out); tensor work per signal k * 2*64*K fp16 flop
-// (0.66 MFLOP at K=1024, k=5; three times that in split3 mode).
+// Roofline: HBM, 4n + 4K bytes per signal (x in, dense Z row out); tensor work per signal k * 2*64*K*3 fp16 flop
+// (1.97 MFLOP at K=1024, k=5; a third of that in screen mode).
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include <cuda_fp16.h>
@@ -362,16 +364,18 @@ __device__ __forceinline__ void update_step(SigState<KNZ>& st, int pick, bool la
 // whose (screened) maximum lies within 2E of the best screened value — all other columns are provably smaller.
 // `thr` = M - 2E and `prow` = the signal's row of piece maxima are lane src's; rbuf is this warp's 64-float scratch.
 __device__ __forceinline__ int resolve_exact(const float (&r)[NF], int src, float thr, const float* prow, int n_pieces,
-                                             const float* __restrict__ Dt, int K, float* rbuf, int lane)
+                                             const float* __restrict__ Dt, int K, float* rbuf, int lane, int* n_cand = nullptr)
 {
     if (lane == src) {
 #pragma unroll
         for (int q = 0; q < NF / 4; ++q) reinterpret_cast<float4*>(rbuf)[q] = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
     }
+    __syncwarp();                                                 // rbuf and the piece maxima are read by the other lanes
     const float thr_s = __shfl_sync(0xffffffffu, thr, src);
     const float* prow_s = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, reinterpret_cast<uintptr_t>(prow), src));
     const float pmv = (lane < n_pieces) ? prow_s[lane * TM] : -1.f;
     unsigned cand = __ballot_sync(0xffffffffu, pmv >= thr_s);
+    if (n_cand) *n_cand += __popc(cand);
     float best = -1.f;
     int bcol = 0x7fffffff;
     while (cand) {
@@ -424,25 +428,33 @@ constexpr int ZB = 16384;                // block of zeros, source of the bulk s
 
 // MODE 0: Batch-OMP (k greedy steps per tile).  MODE 1: 'thresh' — one correlation pass per tile, the scan keeps
 // the k largest signed correlations, coefficients are the exact fp32 dot products with the picked atoms.
-template <int KNZ, int PAIR, bool TIMING, int MODE>
+// SCREEN (MODE 0 only): one fp16 product ranks, certified or resolved exactly (see the header); only the hi planes
+// of the dictionary and of the residuals are staged.
+template <int KNZ, int PAIR, bool TIMING, int MODE, bool SCREEN>
 __global__ void __launch_bounds__(THREADS, 1)
 bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                const uint4* __restrict__ planes, const float* __restrict__ Dt, const float* __restrict__ G,
+               const float* __restrict__ dstats,
                int K, int nch, int64_t N, int k, int n_units /* clusters */, int rounds,
                int32_t* __restrict__ idx, float* __restrict__ val, int32_t* __restrict__ nsel,
                float* __restrict__ Z, int64_t zss, float* __restrict__ scratch)
 {
+    static_assert(!SCREEN || MODE == 0, "screen mode is a Batch-OMP mode");
     using GE = Geo<PAIR>;
     constexpr int NP = CH / 32;
+    constexpr int B_STRIDE = SCREEN ? GE::B_PLANE : GE::B_CHUNK;      // bytes of one chunk of the dictionary in this CTA
+    constexpr int A_STRIDE = SCREEN ? A_PLANE : A_SLOT;               // bytes of one residual tile
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sB = smem;
-    unsigned char* sA = smem + (size_t)nch * GE::B_CHUNK;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + NS * A_SLOT);
+    unsigned char* sA = smem + (size_t)nch * B_STRIDE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + NS * A_STRIDE);
     // bars[slot] a_ready, [2 + slot] tile_begin, [4 + slot] zf_done, [8 + 8 slot + chunk] acc_full,
     // [24 + 8 slot + chunk] acc_empty; then the TMEM base
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
     uint32_t* tile_ready = tmem_slot + 2;              // [slot] signal warps that have published a tile's codes
     unsigned char* zbuf = reinterpret_cast<unsigned char*>(bars) + SMEM_BAR;
+    float* pm_all = reinterpret_cast<float*>(zbuf + NS * ZB);          // [slot][piece][row]       (SCREEN)
+    float* rbuf_all = pm_all + NS * (PM_SLOT / 4);                      // [signal warp][feature]   (SCREEN)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = (PAIR == 2) ? cluster_ctarank() : 0u;
@@ -461,11 +473,12 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
         mbar_init_fence();
     }
     if (warp == 4 * NS) tmem_alloc<PAIR>(smem_u32(tmem_slot), 512);
-    {   // this CTA's share of the dictionary planes: resident for the whole kernel
-        const int items = nch * GE::B_CHUNK / 16;
-        const uint4* src = planes + (size_t)rank * items;
+    {   // this CTA's share of the dictionary planes: resident for the whole kernel (plain loads + st.shared, not TMA:
+        // 64-128 KB once per persistent CTA is not worth a tensor map; the per-tile traffic is the A operand and Z)
+        constexpr int per_chunk = B_STRIDE / 16, src_chunk = GE::B_CHUNK / 16;
+        const uint4* src = planes + (size_t)rank * nch * src_chunk;
         uint4* dst = reinterpret_cast<uint4*>(sB);
-        for (int it = tid; it < items; it += THREADS) dst[it] = __ldg(src + it);
+        for (int it = tid; it < nch * per_chunk; it += THREADS) dst[it] = __ldg(src + (it / per_chunk) * src_chunk + (it % per_chunk));
     }
     for (int it = tid; it < NS * ZB / 16; it += THREADS) reinterpret_cast<uint4*>(zbuf)[it] = make_uint4(0u, 0u, 0u, 0u);
     fence_async_smem();
@@ -486,10 +499,10 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                 const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
                 constexpr uint32_t LBO_A = TM * 16, LBO_B = GE::ROWS_B * 16, SBO = 128;
                 constexpr uint32_t kIdesc = make_idesc<PAIR>();
-                uint32_t u = 0;
                 uint32_t pb0 = 0u, pb1 = 0u, pb2 = 0u, pb3 = 0u, pp0 = 0u, pp1 = 0u, pp2 = 0u, pp3 = 0u;   // who used each TMEM stage last
                 PhaseTimer<TIMING> pt;
                 pt.start();
+                uint32_t u = 0;
                 for (int r = 0; r < rounds; ++r) {
                     for (int j = 0; j < steps; ++j) {
                         const uint32_t q = (uint32_t)(r * steps + j);
@@ -511,18 +524,19 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                                 if (stg == 0) { pb0 = eb; pp0 = q & 1; } else if (stg == 1) { pb1 = eb; pp1 = q & 1; }
                                 else if (stg == 2) { pb2 = eb; pp2 = q & 1; } else { pb3 = eb; pp3 = q & 1; }
                                 const uint32_t d_tmem = tmem_base + stg * CH;
-                                const uint32_t a_hi = a_base + s * A_SLOT, a_lo = a_hi + A_PLANE;
-                                const uint32_t b_hi = b_base + (c * 2) * GE::B_PLANE, b_lo = b_hi + GE::B_PLANE;
-                                // small products first: (lo,hi) (hi,lo) (hi,hi)
+                                const uint32_t a_hi = a_base + s * A_STRIDE, a_lo = a_hi + A_PLANE;
+                                const uint32_t b_hi = b_base + c * B_STRIDE, b_lo = b_hi + GE::B_PLANE;
+                                if constexpr (!SCREEN) {
+#pragma unroll
+                                    for (int ks = 0; ks < NF / 16; ++ks)
+                                        mma_f16<PAIR>(d_tmem, make_desc(a_lo + ks * 2 * LBO_A, LBO_A, SBO), make_desc(b_hi + ks * 2 * LBO_B, LBO_B, SBO), kIdesc, ks > 0);
+#pragma unroll
+                                    for (int ks = 0; ks < NF / 16; ++ks)
+                                        mma_f16<PAIR>(d_tmem, make_desc(a_hi + ks * 2 * LBO_A, LBO_A, SBO), make_desc(b_lo + ks * 2 * LBO_B, LBO_B, SBO), kIdesc, 1);
+                                }
 #pragma unroll
                                 for (int ks = 0; ks < NF / 16; ++ks)
-                                    mma_f16<PAIR>(d_tmem, make_desc(a_lo + ks * 2 * LBO_A, LBO_A, SBO), make_desc(b_hi + ks * 2 * LBO_B, LBO_B, SBO), kIdesc, ks > 0);
-#pragma unroll
-                                for (int ks = 0; ks < NF / 16; ++ks)
-                                    mma_f16<PAIR>(d_tmem, make_desc(a_hi + ks * 2 * LBO_A, LBO_A, SBO), make_desc(b_lo + ks * 2 * LBO_B, LBO_B, SBO), kIdesc, 1);
-#pragma unroll
-                                for (int ks = 0; ks < NF / 16; ++ks)
-                                    mma_f16<PAIR>(d_tmem, make_desc(a_hi + ks * 2 * LBO_A, LBO_A, SBO), make_desc(b_hi + ks * 2 * LBO_B, LBO_B, SBO), kIdesc, 1);
+                                    mma_f16<PAIR>(d_tmem, make_desc(a_hi + ks * 2 * LBO_A, LBO_A, SBO), make_desc(b_hi + ks * 2 * LBO_B, LBO_B, SBO), kIdesc, SCREEN ? (ks > 0) : 1);
                                 commit<PAIR>(bar_local + 8 * (8 + 8 * s + c));        // accumulator ready
                                 pt.lap(10, 0);
                             }
@@ -603,8 +617,11 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
         const int s = warp >> 2;                      // slot
         const int quad = warp & 3;                    // TMEM lane quadrant of this warp
         const int row = quad * 32 + lane;             // row of the tile
-        unsigned char* slotA = sA + s * A_SLOT;
+        unsigned char* slotA = sA + s * A_STRIDE;
         const uint32_t tq = tmem_base + ((uint32_t)(quad * 32) << 16);
+        float* pmcol = pm_all + s * (PM_SLOT / 4) + row;              // this signal's piece maxima: pmcol[piece * TM]
+        float* rbuf = rbuf_all + warp * NF;
+        const float d_err = SCREEN ? __ldg(dstats + 1) : 0.f, d_max = SCREEN ? __ldg(dstats + 2) : 0.f;
         SigState<KNZ> st;
         const int n_keep = k > 2 ? k - 2 : 0;
         float* U = scratch + ((size_t)(blockIdx.x * NS + s) * n_keep) * NF * TM + row;
@@ -631,7 +648,7 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
 #pragma unroll
                 for (int f = 0; f < NF; ++f) st.r[f] = 0.f;
             }
-            store_planes(slotA, row, st.r);
+            st.E = store_planes<SCREEN>(slotA, row, st.r, d_err, d_max);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * s);
@@ -692,43 +709,105 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
             } else {
                 for (int j = 0; j < k; ++j) {
                     // ---- :322 argmax |alpha_j| over all atoms, first maximum
-                    ArgmaxStateR am;
-                    am.run_max = -1.f;
-                    am.run_piece = 0;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) am.kept[i] = 0u;
                     const uint32_t qq = (uint32_t)(r * k + j);
                     const uint32_t u0 = (qq * NS + s) * (uint32_t)nch;
-#pragma unroll 1
-                    for (int c = 0; c < nch; ++c) {
-                        const uint32_t stg = (u0 + c) & (NSTG - 1);
-                        mbar_wait(bar_local + 8 * (8 + 8 * s + c), qq & 1);
-                        fence_after();
-                        pt.lap(2, lane);
-                        const uint32_t ta = tq + stg * CH;
-                        uint32_t b0[32], b1[32];
-                        LYS_TMEM_LD_X32(ta, b0);
-#pragma unroll
-                        for (int sc = 0; sc < NP; sc += 2) {
-                            LYS_TMEM_WAIT_X32(b0);
-                            LYS_TMEM_LD_X32(ta + (sc + 1) * 32, b1);
-                            scan_piece_r(b0, c * NP + sc, am);
-                            LYS_TMEM_WAIT_X32(b1);
-                            if (sc + 2 < NP) LYS_TMEM_LD_X32(ta + (sc + 2) * 32, b0);
-                            else {
-                                fence_before();
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * (24 + 8 * s + c));
-                            }
-                            scan_piece_r(b1, c * NP + sc + 1, am);
-                        }
-                        pt.lap(3, lane);
-                    }
                     const bool last = (j + 1 >= k);
-                    const int run_idx = argmax_finish_r(am);
+                    int run_idx;
+                    if constexpr (!SCREEN) {
+                        ArgmaxStateR am;
+                        am.run_max = -1.f;
+                        am.p2 = -1.f;
+                        am.run_piece = 0;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) am.kept[i] = 0u;
+#pragma unroll 1
+                        for (int c = 0; c < nch; ++c) {
+                            const uint32_t stg = (u0 + c) & (NSTG - 1);
+                            mbar_wait(bar_local + 8 * (8 + 8 * s + c), qq & 1);
+                            fence_after();
+                            pt.lap(2, lane);
+                            const uint32_t ta = tq + stg * CH;
+                            uint32_t b0[32], b1[32];
+                            LYS_TMEM_LD_X32(ta, b0);
+#pragma unroll
+                            for (int sc = 0; sc < NP; sc += 2) {
+                                LYS_TMEM_WAIT_X32(b0);
+                                LYS_TMEM_LD_X32(ta + (sc + 1) * 32, b1);
+                                scan_piece_r<false>(b0, c * NP + sc, am, pmcol);
+                                LYS_TMEM_WAIT_X32(b1);
+                                if (sc + 2 < NP) LYS_TMEM_LD_X32(ta + (sc + 2) * 32, b0);
+                                else {
+                                    fence_before();
+                                    __syncwarp();
+                                    if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * (24 + 8 * s + c));
+                                }
+                                scan_piece_r<false>(b1, c * NP + sc + 1, am, pmcol);
+                            }
+                            pt.lap(3, lane);
+                        }
+                        float s2unused = 0.f;
+                        run_idx = argmax_finish_r<false>(am, &s2unused);
+                    } else {
+                        ArgmaxStateR am;
+                        am.run_max = -1.f;
+                        am.p2 = -1.f;
+                        am.run_piece = 0;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) am.kept[i] = 0u;
+#pragma unroll 1
+                        for (int c = 0; c < nch; ++c) {
+                            const uint32_t stg = (u0 + c) & (NSTG - 1);
+                            mbar_wait(bar_local + 8 * (8 + 8 * s + c), qq & 1);
+                            fence_after();
+                            pt.lap(2, lane);
+                            const uint32_t ta = tq + stg * CH;
+                            uint32_t b0[32], b1[32];
+                            LYS_TMEM_LD_X32(ta, b0);
+#pragma unroll
+                            for (int sc = 0; sc < NP; sc += 2) {
+                                LYS_TMEM_WAIT_X32(b0);
+                                LYS_TMEM_LD_X32(ta + (sc + 1) * 32, b1);
+                                scan_piece_r<true>(b0, c * NP + sc, am, pmcol);
+                                LYS_TMEM_WAIT_X32(b1);
+                                if (sc + 2 < NP) LYS_TMEM_LD_X32(ta + (sc + 2) * 32, b0);
+                                else {
+                                    fence_before();
+                                    __syncwarp();
+                                    if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * (24 + 8 * s + c));
+                                }
+                                scan_piece_r<true>(b1, c * NP + sc + 1, am, pmcol);
+                            }
+                            pt.lap(3, lane);
+                        }
+                        float s2 = 0.f;
+                        run_idx = argmax_finish_r<true>(am, &s2);
+                        // certified if nothing else comes within 2E of the winner; otherwise the warp resolves the
+                        // signal exactly, one uncertified lane at a time
+                        const bool certified = am.run_max - fmaxf(am.p2, s2) > 2.f * st.E;
+                        unsigned todo = __ballot_sync(0xffffffffu, !st.done && !certified);
+                        const float thr = am.run_max - 2.f * st.E;
+                        pt.lap(4, lane);
+                        int n_cand = 0;
+                        if (TIMING) {
+                            const unsigned alive = __ballot_sync(0xffffffffu, !st.done);
+                            if (lane == 0) {
+                                atomicAdd(&g_tc_timing[11], (unsigned long long)__popc(todo));
+                                atomicAdd(&g_tc_timing[13], (unsigned long long)__popc(alive));
+                            }
+                        }
+                        while (todo) {
+                            const int src = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            const int pick = resolve_exact(st.r, src, thr, pmcol, nch * NP, Dt, K, rbuf, lane, TIMING ? &n_cand : nullptr);
+                            if (lane == src) run_idx = pick;
+                        }
+                        if (TIMING && lane == 0) atomicAdd(&g_tc_timing[12], (unsigned long long)n_cand);
+                        pt.lap(6, lane);
+                    }
+                    if ((unsigned)run_idx >= (unsigned)K) run_idx = 0;       // only with NaNs in the signal (np.argmax would return the first NaN)
                     if (!st.done) {
                         switch (j) {
-#define LYS_STEP(JJ) case JJ: if constexpr (JJ < KNZ) update_step<JJ, KNZ>(st, run_idx, last, k, Dt, G, K, U, slotA, row); break;
+#define LYS_STEP(JJ) case JJ: if constexpr (JJ < KNZ) update_step<JJ, KNZ, SCREEN>(st, run_idx, last, k, Dt, G, K, U, slotA, row, d_err, d_max); break;
                             LYS_STEP(0) LYS_STEP(1) LYS_STEP(2) LYS_STEP(3) LYS_STEP(4)
                             LYS_STEP(5) LYS_STEP(6) LYS_STEP(7) LYS_STEP(8) LYS_STEP(9)
 #undef LYS_STEP
@@ -740,7 +819,7 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * s);
                     }
-                    pt.lap(4, lane);
+                    pt.lap(7, lane);
                 }
                 // ---- :354 z = L^-T y, outputs
                 if (live) {
@@ -783,16 +862,69 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
     }
 }
 
+// Dictionary statistics, one CTA: [0] the power-of-two scale s that puts max |s d| in [16, 32) (so that neither the
+// hi nor the lo fp16 plane overflows or goes subnormal whatever the norm of the atoms is), [1] max over atoms of
+// ||s d - rn16(s d)||, [2] max over atoms of ||rn16(s d)|| — the two dictionary-side terms of the screen bound E.
+__global__ void __launch_bounds__(1024)
+dict_stats_kernel(const float* __restrict__ D, int64_t ldd, int n, int K, float* __restrict__ dstats)
+{
+    __shared__ float red[32];
+    __shared__ float s_scale;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    float amax = 0.f;
+    for (int c = t; c < K; c += 1024)
+        for (int f = 0; f < n; ++f) amax = fmaxf(amax, fabsf(__ldg(D + (int64_t)f * ldd + c)));
+    auto block_max = [&](float v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        __syncthreads();
+        if (lane == 0) red[warp] = v;
+        __syncthreads();
+        v = red[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    };
+    amax = block_max(amax);
+    if (t == 0) {
+        int es = 258 - (int)(__float_as_uint(amax) >> 23);           // as store_planes does for a residual
+        es = min(max(es, 1), 254);
+        s_scale = __uint_as_float((uint32_t)es << 23);
+    }
+    __syncthreads();
+    const float sc = s_scale;
+    float emax = 0.f, hmax = 0.f;
+    for (int c = t; c < K; c += 1024) {
+        float e2 = 0.f, h2 = 0.f;
+        for (int f = 0; f < n; ++f) {
+            const float a = __ldg(D + (int64_t)f * ldd + c) * sc;
+            const float h = __half2float(__float2half_rn(a));
+            e2 = fmaf(a - h, a - h, e2);
+            h2 = fmaf(h, h, h2);
+        }
+        emax = fmaxf(emax, e2);
+        hmax = fmaxf(hmax, h2);
+    }
+    emax = block_max(emax);
+    hmax = block_max(hmax);
+    if (t == 0) {
+        dstats[0] = sc;
+        dstats[1] = sqrtf(emax) * 1.0001f;
+        dstats[2] = sqrtf(hmax) * 1.0001f;
+    }
+}
+
 // D (n <= 64, K) fp32 -> (a) the scaled fp16 hi/lo planes in the kernel's shared-memory layout,
 // per CTA of the pair: [rank][chunk][plane][k-chunk][row] 16-byte items; (b) Dt (K, 64) fp32
 // atom-major, zero padded, for the residual / alpha0 gathers.
 template <int PAIR>
 __global__ void prep_dict_kernel(const float* __restrict__ D, int64_t ldd, int n, int K, int nch,
-                                 unsigned char* __restrict__ planes, float* __restrict__ Dt)
+                                 const float* __restrict__ dstats, unsigned char* __restrict__ planes, float* __restrict__ Dt)
 {
     using GE = Geo<PAIR>;
     const int item = blockIdx.x * blockDim.x + threadIdx.x;        // one 16-byte chunk of one atom
     if (item >= K * (NF / 8)) return;
+    const float dscale = __ldg(dstats);
     const int atom = item % K, kc = item / K;
     const int c = atom / CH, nn = atom % CH, h = nn / GE::ROWS_B, row = nn % GE::ROWS_B;
     float v[8];
@@ -805,7 +937,7 @@ __global__ void prep_dict_kernel(const float* __restrict__ D, int64_t ldd, int n
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const float a = v[2 * e] * kDictScale, b = v[2 * e + 1] * kDictScale;
+        const float a = v[2 * e] * dscale, b = v[2 * e + 1] * dscale;
         const __half2 hh = __floats2half2_rn(a, b);
         const float2 hf = __half22float2(hh);
         const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
@@ -827,18 +959,44 @@ size_t dt_bytes(int K) { return (size_t)K * NF * sizeof(float); }
 // orthonormalised directions u_0..u_{k-3} of every signal in flight: [CTA][slot][vector][feature][signal]
 size_t scratch_bytes(int k) { return (size_t)sm_count() * MAX_SLOTS * (k > 2 ? k - 2 : 0) * NF * TM * sizeof(float); }
 
-template <int KNZ, int PAIR, int MODE = 0>
-int launch_tc(const float* X, int64_t xfs, int64_t xss, int n, const void* planes, const float* Dt, const float* G,
+struct FusedWs { unsigned char* planes; float* Dt; float* dstats; float* scratch; };
+FusedWs carve_ws(void* workspace, int K)
+{
+    FusedWs w;
+    unsigned char* p = reinterpret_cast<unsigned char*>(workspace);
+    w.planes = p; p += align_up(planes_bytes(K), 256);
+    w.Dt = reinterpret_cast<float*>(p); p += align_up(dt_bytes(K), 256);
+    w.dstats = reinterpret_cast<float*>(p); p += 256;
+    w.scratch = reinterpret_cast<float*>(p);
+    return w;
+}
+
+int prepare_dictionary(const float* D, int64_t ldd, int n, int K, const FusedWs& w, cudaStream_t stream)
+{
+    const int pair = (K > 512) ? 2 : 1;
+    const int nch = K / CH;
+    const int items = K * (NF / 8);
+    dict_stats_kernel<<<1, 1024, 0, stream>>>(D, ldd, n, K, w.dstats);
+    LYS_LAUNCH_CHECK("dict_stats_kernel");
+    if (pair == 2) prep_dict_kernel<2><<<(items + 255) / 256, 256, 0, stream>>>(D, ldd, n, K, nch, w.dstats, w.planes, w.Dt);
+    else prep_dict_kernel<1><<<(items + 255) / 256, 256, 0, stream>>>(D, ldd, n, K, nch, w.dstats, w.planes, w.Dt);
+    LYS_LAUNCH_CHECK("prep_dict_kernel");
+    return LYS_OK;
+}
+
+template <int KNZ, int PAIR, int MODE, bool SCREEN>
+int launch_tc(const float* X, int64_t xfs, int64_t xss, int n, const FusedWs& w, const float* G,
               int K, int64_t N, int k, int32_t* idx, float* val, int32_t* nsel, float* Z, int64_t zss,
-              float* scratch, cudaStream_t stream)
+              cudaStream_t stream)
 {
     using GE = Geo<PAIR>;
     const int nch = K / CH;
-    const size_t smem = (size_t)nch * GE::B_CHUNK + (size_t)NS * A_SLOT + SMEM_BAR + NS * ZB;
+    const size_t smem = (size_t)nch * (SCREEN ? GE::B_PLANE : GE::B_CHUNK) + (size_t)NS * (SCREEN ? A_PLANE : A_SLOT) + SMEM_BAR + NS * ZB +
+                        (SCREEN ? (size_t)NS * PM_SLOT + RBUF : 0);
 #ifdef LYS_BRINGUP      // phase timers: only in the bring-up build (python -m lyssandra_b200._build --bringup)
-    auto kern = bomp_tc_kernel<KNZ, PAIR, (MODE == 0), MODE>;
+    auto kern = bomp_tc_kernel<KNZ, PAIR, (MODE == 0), MODE, SCREEN>;
 #else
-    auto kern = bomp_tc_kernel<KNZ, PAIR, false, MODE>;
+    auto kern = bomp_tc_kernel<KNZ, PAIR, false, MODE, SCREEN>;
 #endif
     LYS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n_tiles = (N + TM - 1) / TM;
@@ -863,10 +1021,22 @@ int launch_tc(const float* X, int64_t xfs, int64_t xss, int n, const void* plane
     units = (int)std::max<int64_t>(1, std::min<int64_t>(units, (n_tiles + tiles_per_unit - 1) / tiles_per_unit));
     const int rounds = (int)((n_tiles + (int64_t)units * tiles_per_unit - 1) / ((int64_t)units * tiles_per_unit));
     cfg.gridDim = dim3((unsigned)(units * PAIR), 1, 1);
-    LYS_CUDA(cudaLaunchKernelEx(&cfg, kern, X, xfs, xss, n, reinterpret_cast<const uint4*>(planes), Dt, G, K, nch, N, k,
-                                units, rounds, idx, val, nsel, Z, zss, scratch));
+    LYS_CUDA(cudaLaunchKernelEx(&cfg, kern, X, xfs, xss, n, reinterpret_cast<const uint4*>(w.planes), (const float*)w.Dt, G,
+                                (const float*)w.dstats, K, nch, N, k, units, rounds, idx, val, nsel, Z, zss, w.scratch));
     LYS_LAUNCH_CHECK("bomp_tc_kernel");
     return LYS_OK;
+}
+
+template <int MODE, bool SCREEN>
+int launch_by_shape(const float* X, int64_t xfs, int64_t xss, int n, const FusedWs& w, const float* G,
+                    int K, int64_t N, int k, int32_t* idx, float* val, int32_t* nsel, float* Z, int64_t zss, cudaStream_t stream)
+{
+    const bool pair = K > 512;
+    if (k <= 5)
+        return pair ? launch_tc<5, 2, MODE, SCREEN>(X, xfs, xss, n, w, G, K, N, k, idx, val, nsel, Z, zss, stream)
+                    : launch_tc<5, 1, MODE, SCREEN>(X, xfs, xss, n, w, G, K, N, k, idx, val, nsel, Z, zss, stream);
+    return pair ? launch_tc<10, 2, MODE, SCREEN>(X, xfs, xss, n, w, G, K, N, k, idx, val, nsel, Z, zss, stream)
+                : launch_tc<10, 1, MODE, SCREEN>(X, xfs, xss, n, w, G, K, N, k, idx, val, nsel, Z, zss, stream);
 }
 
 }  // namespace
@@ -874,39 +1044,28 @@ int launch_tc(const float* X, int64_t xfs, int64_t xss, int n, const void* plane
 size_t bomp_fused_workspace_bytes(int n, int K, int64_t, int k)
 {
     if (!fused_shape_ok(n, K, k)) return 0;
-    return align_up(planes_bytes(K), 256) + align_up(dt_bytes(K), 256) + align_up(scratch_bytes(k), 256) + 256;
+    return align_up(planes_bytes(K), 256) + align_up(dt_bytes(K), 256) + 256 + align_up(scratch_bytes(k), 256) + 256;
 }
 
-int bomp_fused_launch_count(int n, int K, int64_t, int k) { return fused_shape_ok(n, K, k) ? 2 : 0; }
+int bomp_fused_launch_count(int n, int K, int64_t, int k) { return fused_shape_ok(n, K, k) ? 3 : 0; }
 
 // returns LYS_EUNSUPPORTED for shapes this path is not built for (the caller then takes the
-// two-kernel path); Z must be signal-major (atom stride 1) here, other layouts are filled by the caller
+// two-kernel path); Z must be signal-major (atom stride 1) here, other layouts are filled by the caller.
+// screen != 0 selects the one-product screened correlations (see the header); the codes are the same.
 int bomp_encode_fused(const float* X, int64_t xfs, int64_t xss, const float* D, int64_t ldd, const float* G,
                       int n, int K, int64_t N, int k, int32_t* idx, float* val, int32_t* nsel,
-                      float* Z, int64_t zas, int64_t zss, void* workspace, size_t workspace_bytes, cudaStream_t stream)
+                      float* Z, int64_t zas, int64_t zss, void* workspace, size_t workspace_bytes, int screen, cudaStream_t stream)
 {
     if (!fused_shape_ok(n, K, k)) return LYS_EUNSUPPORTED;
     if (Z && (zas != 1 || (zss % 4) != 0 || (reinterpret_cast<uintptr_t>(Z) & 15) != 0)) return LYS_EUNSUPPORTED;
     if (workspace_bytes < bomp_fused_workspace_bytes(n, K, N, k)) return LYS_EWORKSPACE;
-    unsigned char* planes = reinterpret_cast<unsigned char*>(workspace);
-    float* Dt = reinterpret_cast<float*>(planes + align_up(planes_bytes(K), 256));
-    float* scratch = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Dt) + align_up(dt_bytes(K), 256));
-    const int pair = (K > 512) ? 2 : 1;
-    const int nch = K / CH;
-    const int items = K * (NF / 8);
-    if (pair == 2) prep_dict_kernel<2><<<(items + 255) / 256, 256, 0, stream>>>(D, ldd, n, K, nch, planes, Dt);
-    else prep_dict_kernel<1><<<(items + 255) / 256, 256, 0, stream>>>(D, ldd, n, K, nch, planes, Dt);
-    LYS_LAUNCH_CHECK("prep_dict_kernel");
+    const FusedWs w = carve_ws(workspace, K);
+    int rc = prepare_dictionary(D, ldd, n, K, w, stream);
+    if (rc) return rc;
     cudaEvent_t stop_ev;
     const bool prof = profile_begin(stream, "bomp_tc_kernel", &stop_ev);
-    int rc;
-    if (k <= 5) {
-        rc = (pair == 2) ? launch_tc<5, 2>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream)
-                         : launch_tc<5, 1>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream);
-    } else {
-        rc = (pair == 2) ? launch_tc<10, 2>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream)
-                         : launch_tc<10, 1>(X, xfs, xss, n, planes, Dt, G, K, N, k, idx, val, nsel, Z, zss, scratch, stream);
-    }
+    rc = screen ? launch_by_shape<0, true>(X, xfs, xss, n, w, G, K, N, k, idx, val, nsel, Z, zss, stream)
+                : launch_by_shape<0, false>(X, xfs, xss, n, w, G, K, N, k, idx, val, nsel, Z, zss, stream);
     if (prof) cudaEventRecord(stop_ev, stream);
     return rc;
 }
@@ -914,7 +1073,7 @@ int bomp_encode_fused(const float* X, int64_t xfs, int64_t xss, const float* D, 
 size_t thresh_fused_workspace_bytes(int n, int K, int64_t, int k)
 {
     if (!fused_shape_ok(n, K, k)) return 0;
-    return align_up(planes_bytes(K), 256) + align_up(dt_bytes(K), 256) + 256;
+    return align_up(planes_bytes(K), 256) + align_up(dt_bytes(K), 256) + 256 + 256;
 }
 
 // 'thresh' coder through the fused kernel (MODE 1): same shapes and Z layout rules as bomp_encode_fused
@@ -925,19 +1084,11 @@ int thresh_encode_fused(const float* X, int64_t xfs, int64_t xss, const float* D
     if (!fused_shape_ok(n, K, k)) return LYS_EUNSUPPORTED;
     if (Z && (zas != 1 || (zss % 4) != 0 || (reinterpret_cast<uintptr_t>(Z) & 15) != 0)) return LYS_EUNSUPPORTED;
     if (workspace_bytes < thresh_fused_workspace_bytes(n, K, N, k)) return LYS_EWORKSPACE;
-    unsigned char* planes = reinterpret_cast<unsigned char*>(workspace);
-    float* Dt = reinterpret_cast<float*>(planes + align_up(planes_bytes(K), 256));
-    const int pair = (K > 512) ? 2 : 1;
-    const int nch = K / CH;
-    const int items = K * (NF / 8);
-    if (pair == 2) prep_dict_kernel<2><<<(items + 255) / 256, 256, 0, stream>>>(D, ldd, n, K, nch, planes, Dt);
-    else prep_dict_kernel<1><<<(items + 255) / 256, 256, 0, stream>>>(D, ldd, n, K, nch, planes, Dt);
-    LYS_LAUNCH_CHECK("prep_dict_kernel");
-    if (k <= 5)
-        return (pair == 2) ? launch_tc<5, 2, 1>(X, xfs, xss, n, planes, Dt, nullptr, K, N, k, idx, val, nsel, Z, zss, nullptr, stream)
-                           : launch_tc<5, 1, 1>(X, xfs, xss, n, planes, Dt, nullptr, K, N, k, idx, val, nsel, Z, zss, nullptr, stream);
-    return (pair == 2) ? launch_tc<10, 2, 1>(X, xfs, xss, n, planes, Dt, nullptr, K, N, k, idx, val, nsel, Z, zss, nullptr, stream)
-                       : launch_tc<10, 1, 1>(X, xfs, xss, n, planes, Dt, nullptr, K, N, k, idx, val, nsel, Z, zss, nullptr, stream);
+    FusedWs w = carve_ws(workspace, K);
+    w.scratch = nullptr;
+    const int rc = prepare_dictionary(D, ldd, n, K, w, stream);
+    if (rc) return rc;
+    return launch_by_shape<1, false>(X, xfs, xss, n, w, nullptr, K, N, k, idx, val, nsel, Z, zss, stream);
 }
 
 }  // namespace lys

@@ -54,6 +54,10 @@ def ksvd_dict_learn(X, n_atoms, init_dict="data", sparse_coder=None, max_iter=20
     replicated.  Encode needs no collective; the sweep all-reduces its per-atom sums inside the
     kernel; the error is one scalar all-reduce; 'data' initialisation and unused-atom
     replacement draw from rank 0's shard and are broadcast."""
+    if max_iter is None or int(max_iter) < 0:
+        # the reference's ksvd_coder default (max_iter=None, ksvd.py:240) only "works" on Python 2, where
+        # `0 < None` is False and the loop is silently skipped; say what is wrong instead
+        raise ValueError("max_iter must be a non-negative integer (ksvd_coder's default None never ran an iteration in the reference)")
     if not approx:
         raise NotImplementedError("exact K-SVD (approx=False) is outside this engine's scope; pass approx=True")
     if non_neg:

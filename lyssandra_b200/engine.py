@@ -104,9 +104,10 @@ def gram(D):
     return G
 
 
-def bomp_encode(X, D, k, G=None, dense=False):
+def bomp_encode(X, D, k, G=None, dense=False, screen=False):
     """Batch-OMP of the columns of X over D (device tensors).  Returns SparseCodes and, if
-    ``dense``, also Z as a (K, N) transposed view (lyssa/sparse_coding.py:629-635,:302-367)."""
+    ``dense``, also Z as a (K, N) transposed view (lyssa/sparse_coding.py:629-635,:302-367).
+    ``screen`` selects the one-product screened correlations of the fused kernel (LYS_BOMP_SCREEN, same codes; A/B checks)."""
     lib = nat.load()
     n, N = X.shape
     n2, K = D.shape
@@ -125,9 +126,10 @@ def bomp_encode(X, D, k, G=None, dense=False):
         Zt = torch.empty((N, K), dtype=torch.float32, device=dev) if dense else None
         wsb = lib.lys_bomp_workspace_bytes(n, K, N, k)
         ws = workspace(dev, wsb)
-        nat.check(lib.lys_bomp_encode(
+        nat.check(lib.lys_bomp_encode_ex(
             _ptr(X), X.stride(0), X.stride(1), _ptr(D), D.stride(0), _ptr(G), n, K, N, k,
-            _ptr(idx), _ptr(val), _ptr(nsel), _ptr(Zt), 1, K, _ptr(ws), ws.numel(), _stream_ptr(dev)))
+            _ptr(idx), _ptr(val), _ptr(nsel), _ptr(Zt), 1, K, _ptr(ws), ws.numel(),
+            nat.BOMP_SCREEN if screen else 0, _stream_ptr(dev)))
     codes = SparseCodes(idx, val, nsel, K)
     if dense:
         return codes, Zt.t()

@@ -135,6 +135,74 @@ def batch_omp(X, Alpha, D, Gram, n_nonzero_coefs=None, tol=None, trace=None):
     return Z
 
 
+def _omp(x, D, Gram, alpha, n_nonzero_coefs=None, tol=None):
+    """Plain OMP of one signal — lyssa/sparse_coding.py:19-57.  Stopping rule (:27-34): with n_nonzero_coefs the
+    tolerance is forced to 1e-10 and the loop runs while i < n_nonzero_coefs and ||r|| > 1e-10; with only ``tol`` it
+    runs while ||r|| >= tol.  Per step: first-maximum argmax of |alpha| (:40); stop if already selected (:41-42);
+    z = inv(G[I,I]) (D^T x)[I] with the TRUE Gram (no unit-norm assumption, unlike batch_omp) (:45-53); r = x - D_I z,
+    alpha = D^T r (:54-55).  A singular G[I,I] (LinAlgError) stops with the previous z (:48-51)."""
+    n_atoms = D.shape[1]
+    support = np.array([]).astype(int)
+    z = np.zeros(n_atoms)
+    r = np.copy(x)
+    i = 0
+    if n_nonzero_coefs is not None:
+        tol = 1e-10
+
+        def cont():
+            return i < n_nonzero_coefs and np.linalg.norm(r) > tol
+    else:
+        def cont():
+            return np.linalg.norm(r) >= tol
+    while cont():
+        pick = np.argmax(np.abs(alpha))                              # :40
+        if pick in support:                                          # :41-42
+            break
+        support = np.append(support, pick)
+        G = np.atleast_2d(Gram[support, :][:, support])              # :45-46
+        try:
+            G_inv = np.linalg.inv(G)                                 # :48
+        except np.linalg.LinAlgError:
+            break
+        z[support] = np.dot(G_inv, np.dot(D.T, x)[support])          # :53
+        r = x - np.dot(D[:, support], z[support])                    # :54
+        alpha = np.dot(D.T, r)                                       # :55
+        i += 1
+    return z
+
+
+def omp(X, Alpha, D, Gram, n_nonzero_coefs=None, tol=None):
+    """lyssa/sparse_coding.py:60-66: _omp over the columns of X."""
+    n_atoms, n_signals = D.shape[1], X.shape[1]
+    Z = np.zeros((n_atoms, n_signals))
+    for i in range(n_signals):
+        Z[:, i] = _omp(X[:, i], D, Gram, Alpha[:, i], n_nonzero_coefs=n_nonzero_coefs, tol=tol)
+    return Z
+
+
+def soft_thresholding(Alpha, nonzero_percentage=None, n_nonzero_coefs=None):
+    """lyssa/feature_encoding.py:26-37 — line for line the same computation as ``thresholding``
+    (sparse_coding.py:416-425): the n_nonzero_coefs largest SIGNED correlations of every signal."""
+    return thresholding(Alpha, nonzero_percentage=nonzero_percentage, n_nonzero_coefs=n_nonzero_coefs)
+
+
+class feature_encoder(object):
+    """lyssa/feature_encoding.py:40-89: algorithm 'soft_thresholding' = soft_thresholding(D^T X)."""
+
+    def __init__(self, algorithm=None, params=None, n_jobs=1, verbose=True, mmap=False):
+        self.algorithm, self.params = algorithm, ({} if params is None else params)
+        self.n_jobs, self.verbose, self.mmap = n_jobs, verbose, mmap
+
+    def encode(self, X, D):
+        return self.__call__(X, D)
+
+    def __call__(self, X, D):
+        if self.algorithm != "soft_thresholding":                   # the reference leaves `func` unbound here (:64-70)
+            raise NameError("feature_encoder: unknown algorithm %r" % (self.algorithm,))
+        return soft_thresholding(np.dot(D.T, X), nonzero_percentage=self.params.get("nonzero_percentage"),
+                                 n_nonzero_coefs=self.params.get("n_nonzero_coefs"))
+
+
 def _bomp_job(args):
     alpha_cols, gram, k = args
     return batch_omp(None, alpha_cols, None, gram, n_nonzero_coefs=k)
@@ -206,10 +274,13 @@ class sparse_encoder(object):
                                           n_nonzero_coefs=self.params.get("n_nonzero_coefs"),
                                           n_iter=self.params.get("n_iter"))
             return Z
+        if self.algorithm == "omp":                                  # :618-625
+            gram = np.dot(D.T, D)
+            alpha = np.dot(D.T, X)
+            return omp(X, alpha, D, gram, n_nonzero_coefs=self.params.get("n_nonzero_coefs"), tol=self.params.get("tol"))
         if self.algorithm != "bomp":
-            if self.algorithm in ("omp", "nnomp", "group_omp", "sparse_group_omp",
-                                  "somp", "lasso", "llc"):
-                raise NotImplementedError("oracle restates only 'bomp', 'thresh' and 'iht'")
+            if self.algorithm in ("nnomp", "group_omp", "sparse_group_omp", "somp", "lasso", "llc"):
+                raise NotImplementedError("oracle restates only 'omp', 'bomp', 'thresh' and 'iht'")
             raise ValueError("Sparse optimizer not found.")
         k = self.params.get("n_nonzero_coefs")
         n_atoms, n_signals = D.shape[1], X.shape[1]

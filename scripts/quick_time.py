@@ -16,17 +16,18 @@ G = torch.empty((K, K), device=dev)
 wsb = lib.lys_bomp_workspace_bytes(n, K, N, k); ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
 st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 _native.check(lib.lys_gram(D.data_ptr(), K, n, K, G.data_ptr(), st))
-def enc(dense):
-    _native.check(lib.lys_bomp_encode(X.data_ptr(), X.stride(0), X.stride(1), D.data_ptr(), K, G.data_ptr(), n, K, N, k,
-                                      idx.data_ptr(), val.data_ptr(), nsel.data_ptr(), Zt.data_ptr() if dense else None, 1, K, ws.data_ptr(), wsb, st))
-res = []
-for dense in (True, False):
-    for _ in range(3): enc(dense)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10): enc(dense)
-    e1.record(); torch.cuda.synchronize()
-    res.append(e0.elapsed_time(e1) / 10)
-chk = int(idx.sum().item())
-print("%s ver=%s K=%d k=%d: dense %.3f ms, sparse %.3f ms (idx checksum %d)" % (os.path.basename(os.environ.get("LYSSA_B200_LIB", "default")), os.environ.get("LYS_TC_VER", "1"), K, k, res[0], res[1], chk), flush=True)
+def enc(dense, flags):
+    _native.check(lib.lys_bomp_encode_ex(X.data_ptr(), X.stride(0), X.stride(1), D.data_ptr(), K, G.data_ptr(), n, K, N, k,
+                                         idx.data_ptr(), val.data_ptr(), nsel.data_ptr(), Zt.data_ptr() if dense else None, 1, K, ws.data_ptr(), wsb, flags, st))
+for flags, name in ((0, "split3"), (_native.BOMP_SCREEN, "screen")):
+    res = []
+    for dense in (True, False):
+        for _ in range(3): enc(dense, flags)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10): enc(dense, flags)
+        e1.record(); torch.cuda.synchronize()
+        res.append(e0.elapsed_time(e1) / 10)
+    chk = int(idx.sum().item())
+    print("%s %s K=%d k=%d: dense %.3f ms, sparse %.3f ms (idx checksum %d)" % (os.path.basename(os.environ.get("LYSSA_B200_LIB", "default")), name, K, k, res[0], res[1], chk), flush=True)

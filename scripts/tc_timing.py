@@ -16,9 +16,10 @@ G = torch.empty((K, K), device=dev)
 wsb = lib.lys_bomp_workspace_bytes(n, K, N, k); ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
 st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 _native.check(lib.lys_gram(D.data_ptr(), K, n, K, G.data_ptr(), st))
+FLAGS = _native.BOMP_SCREEN if os.environ.get("TC_SCREEN") else 0
 def enc(dense=True):
-    _native.check(lib.lys_bomp_encode(X.data_ptr(), X.stride(0), X.stride(1), D.data_ptr(), K, G.data_ptr(), n, K, N, k,
-                                      idx.data_ptr(), val.data_ptr(), nsel.data_ptr(), Zt.data_ptr() if dense else None, 1, K, ws.data_ptr(), wsb, st))
+    _native.check(lib.lys_bomp_encode_ex(X.data_ptr(), X.stride(0), X.stride(1), D.data_ptr(), K, G.data_ptr(), n, K, N, k,
+                                         idx.data_ptr(), val.data_ptr(), nsel.data_ptr(), Zt.data_ptr() if dense else None, 1, K, ws.data_ptr(), wsb, FLAGS, st))
 out = (ctypes.c_ulonglong * 16)()
 dbg = lib.lys_debug_tc_timing
 trace = (ctypes.c_ulonglong * 8192)(); ntr = ctypes.c_uint()
@@ -32,8 +33,10 @@ for dense in (True, False):
         for i in range(min(int(ntr.value), 8192)):
             e = int(trace[i]); fh.write("%d %d %d\n" % (e >> 8, (e >> 4) & 15, e & 15))
     v = [int(x) for x in out]
-    names = ["tile start", "zero fill", "wait acc_full", "scan", "finish+update", "outputs", "", "", "mma: wait a_ready", "mma: wait acc_empty", "mma: issue"]
-    print("slots=%s K=%d k=%d dense=%s: %.3f ms" % (os.environ.get("LYS_TC_SLOTS", "3"), K, k, dense, e0.elapsed_time(e1)))
-    tot_e = sum(v[:6]); tot_m = sum(v[8:11])
+    names = ["tile start", "zero fill", "wait acc_full", "scan", "finish", "outputs", "resolve", "update", "mma: wait a_ready", "mma: wait acc_empty", "mma: issue"]
+    print("screen=%s K=%d k=%d dense=%s: %.3f ms" % (bool(FLAGS), K, k, dense, e0.elapsed_time(e1)))
+    tot_e = sum(v[:8]); tot_m = sum(v[8:11])
     for i, nm in enumerate(names):
-        if nm: print("   %-20s %6.2f %%" % (nm, 100.0 * v[i] / (tot_e if i < 6 else tot_m)))
+        if nm: print("   %-28s %6.2f %%  (%.0f cycles per warp-step)" % (nm, 100.0 * v[i] / (tot_e if i < 8 else tot_m), v[i] / (N / 32.0 * k)))
+    if v[13]:
+        print("   signal-steps %d, uncertified %d (%.2f %%), candidate pieces per uncertified %.2f" % (v[13], v[11], 100.0 * v[11] / v[13], v[12] / max(v[11], 1)))

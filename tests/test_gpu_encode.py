@@ -247,3 +247,64 @@ def test_fused_kernel_dense_layouts():
         assert np.array_equal(Zd, ref)
         if o[2].shape[1] > K:
             assert np.all(o[2][:, K:] == 7.0)                           # padding columns untouched
+
+
+def test_screen_and_split3_correlations_give_identical_codes():
+    """The default fused path computes fp32-faithful correlations with three fp16 products; the LYS_BOMP_SCREEN path
+    ranks with ONE product and certifies or exactly resolves every argmax.  Both must select the same atoms on
+    every column that is not a near-tie in float64 — and, because everything after the argmax is the same fp32 code,
+    then return bit-identical coefficients.  cfg2 data, 262144 columns, k = 5 and k = 10; K = 512 (single-CTA variant)."""
+    for n, K, N, k, seed in ((64, 1024, 262144, 5, 0), (64, 1024, 65536, 10, 3), (64, 512, 65536, 5, 4), (40, 768, 20000, 7, 5)):
+        Xh = lo.synthetic_patches(N, n, seed=seed); Dh = lo.synthetic_dictionary(K, n, seed=seed + 1)
+        X = torch.from_numpy(np.ascontiguousarray(Xh.T)).to(DEV).t()
+        D = torch.from_numpy(Dh).to(DEV)
+        a = engine.bomp_encode(X, D, k)
+        b = engine.bomp_encode(X, D, k, screen=True)
+        same = (a.idx == b.idx).all(dim=1)
+        differ = torch.nonzero(~same).flatten().cpu().numpy()
+        if differ.size:
+            # a split-product value carries a 2^-22 relative error, so the two paths may part on float64 near-ties only
+            _, _, ok = _oracle_ok(Xh[:, differ], Dh, k)
+            assert not ok.any(), "paths differ on %d well-separated columns" % int(ok.sum())
+        assert differ.size <= N // 20000 + 1
+        assert torch.equal(a.val[same], b.val[same]) and torch.equal(a.nsel[same], b.nsel[same])
+
+
+@pytest.mark.parametrize("n,K,k", [(64, 1024, 5), (64, 512, 10), (128, 1024, 5), (33, 300, 4)])
+def test_nan_and_inf_signals_are_memory_safe(n, K, k):
+    """np.argmax on a NaN column returns an index in range (the first NaN) and the reference just produces NaN codes
+    (sparse_coding.py:322); here every kernel family (fused, two-kernel, generic) must stay in bounds: indices in
+    [-1, K), the clean columns unaffected, no sticky CUDA error."""
+    N = 700
+    Xh = lo.synthetic_patches(N, n, seed=9).copy(); Dh = lo.synthetic_dictionary(K, n, seed=10)
+    bad = [3, 130, 131, 699]
+    Xh[5, 3] = np.nan; Xh[:, 130] = np.nan; Xh[0, 131] = np.inf; Xh[7, 699] = -np.inf
+    X = torch.from_numpy(np.ascontiguousarray(Xh)).to(DEV); D = torch.from_numpy(Dh).to(DEV)
+    codes, Z = engine.bomp_encode(X, D, k, dense=True)
+    torch.cuda.synchronize()
+    idx = codes.idx.cpu().numpy()
+    assert idx.min() >= -1 and idx.max() < K
+    good = np.setdiff1d(np.arange(N), bad)
+    clean = engine.bomp_encode(torch.from_numpy(np.ascontiguousarray(Xh[:, good])).to(DEV), D, k)
+    assert np.array_equal(idx[good], clean.idx.cpu().numpy())
+    assert torch.equal(codes.val[torch.as_tensor(good, device=DEV)], clean.val)
+    assert bool(torch.isfinite(Z.t()[torch.as_tensor(good, device=DEV)]).all())
+
+
+def test_dictionary_scale_does_not_matter_to_the_fused_path():
+    """The fp16 planes of the dictionary use a power-of-two scale derived from max|D| (a fixed scale overflowed for
+    |d| > 2047): a dictionary scaled by 4096 or 1/4096 must select like the unit-norm one.  'thresh' does not need unit
+    norm in the reference (sparse_coding.py:416-425), so this matters for the fused thresholding coder as well."""
+    n, K, N, k = 64, 1024, 4000, 5
+    Xh = lo.synthetic_patches(N, n, seed=13); Dh = lo.synthetic_dictionary(K, n, seed=14)
+    X = torch.from_numpy(np.ascontiguousarray(Xh)).to(DEV)
+    base = engine.thresh_encode(X, torch.from_numpy(Dh).to(DEV), k)
+    for scale in (4096.0, 1.0 / 4096.0):
+        c = engine.thresh_encode(X, torch.from_numpy(Dh * np.float32(scale)).to(DEV), k)
+        same = (c.idx == base.idx).all(dim=1)
+        assert int((~same).sum()) <= N // 500
+        assert torch.allclose(c.val[same], base.val[same] * scale, rtol=1e-6, atol=0)
+    # Batch-OMP itself assumes unit-norm atoms (quirk Q1), so only the first pick is scale-free: k = 1
+    b1 = engine.bomp_encode(X, torch.from_numpy(Dh).to(DEV), 1)
+    b2 = engine.bomp_encode(X, torch.from_numpy(Dh * np.float32(4096.0)).to(DEV), 1)
+    assert int((b1.idx != b2.idx).sum()) <= N // 500
