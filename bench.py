@@ -289,34 +289,67 @@ def scspm_images_per_s(dev, rank, world, n_total=10000, size=256, chunk=250):
     return ms, parity
 
 
-def odl_minibatch_ms(dev, n=128, K=2048, k=5, b=4096):
-    """One ODL minibatch in the shape of BASELINE cfg4 (SIFT-like 128-d descriptors, D 128x2048, minibatch 4096):
-    encode -> A,B accumulation (beta = 0.9) -> dictionary update; median of 8 minibatches, stage times by CUDA events."""
+def odl_minibatch_ms(dev, rank, world, n=128, K=2048, k=5, b=4096, n_mb=24):
+    """ODL at BASELINE cfg4 (SIFT-like 128-d descriptors, D 128x2048, minibatch 4096, beta = 0.9): the minibatch is split
+    over the ranks, each rank encodes its b/world signals, the slices are all-gathered as (signal, idx, val) and the
+    statistics + dictionary update run replicated in a fixed order (bit-identical D on every rank).  Returns
+    (median ms per minibatch through online_dict_learn's own loop, stage split on one minibatch, parity dict or None)."""
     import torch
+    import torch.distributed as dist
     from lyssandra_b200 import engine
+    from lyssandra_b200.distributed import DistContext
+    from lyssandra_b200.dict_learning import online_dict_learn
     from lyssandra_b200.sparse_coding import sparse_encoder
     from oracle import lyssa_oracle as lo
-    X = torch.from_numpy(np.ascontiguousarray(lo.synthetic_descriptors(b * 8, n, seed=0).T)).to(dev).t()
+    ctx = DistContext.from_env_or_group()
+    b_loc = b // world
+    Xfull = np.ascontiguousarray(lo.synthetic_descriptors(b * n_mb, n, seed=0).T)              # (b*n_mb, n), minibatch-major
+    mine = np.concatenate([Xfull[m * b + rank * b_loc: m * b + (rank + 1) * b_loc] for m in range(n_mb)], axis=0)
+    X = torch.from_numpy(mine).to(dev).t()                                                  # this rank's slice of every minibatch
     rng = np.random.default_rng(1)
-    D = torch.from_numpy(np.ascontiguousarray(lo.norm_cols(np.abs(rng.standard_normal((n, K)))).astype(np.float32))).to(dev)
-    A = torch.zeros((K, K), device=dev); B = torch.zeros((n, K), device=dev)
+    D0 = torch.from_numpy(np.ascontiguousarray(lo.norm_cols(np.abs(rng.standard_normal((n, K)))).astype(np.float32))).to(dev)
     enc = sparse_encoder("bomp", {"n_nonzero_coefs": k}, verbose=False)
 
+    def run(Xs, bs, dctx):
+        D = D0.clone()
+        torch.cuda.synchronize(dev); ctx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        D, A, B = online_dict_learn(Xs, K, sparse_coder=enc, batch_size=bs, D_init=D, beta=0.9, n_epochs=1, dist=dctx)
+        e1.record(); torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n_mb, D, A
+
+    run(X, b_loc, ctx if world > 1 else None)                                               # warm-up
+    ms, D, A = run(X, b_loc, ctx if world > 1 else None)
+    ms2, D_again, _ = run(X, b_loc, ctx if world > 1 else None)
+    reproducible = bool(torch.equal(D, D_again))
+    # stage split of one minibatch (this rank's slice encoded, whole minibatch accumulated)
     def timed(fn):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(dev); e0.record(); out = fn(); e1.record(); torch.cuda.synchronize(dev)
         return e0.elapsed_time(e1), out
-
-    st = {"encode": [], "accumulate": [], "update": []}
-    for it in range(9):
-        Xb = X[:, (it % 8) * b:(it % 8 + 1) * b]
-        t1, codes = timed(lambda: enc.encode_sparse(Xb, D))
-        t2, _ = timed(lambda: engine.odl_accumulate_(Xb, codes, 0.9, A, B))
-        t3, _ = timed(lambda: engine.odl_update_dict_(D, A, B))
+    Xb = torch.from_numpy(Xfull[:b]).to(dev).t()
+    Ds = D0.clone(); As = torch.zeros((K, K), device=dev); Bs = torch.zeros((n, K), device=dev)
+    st = {"encode_slice": [], "accumulate": [], "update": []}
+    for it in range(6):
+        t1, _ = timed(lambda: enc.encode_sparse(Xb[:, :b_loc], Ds))
+        codes = enc.encode_sparse(Xb, Ds)
+        t2, _ = timed(lambda: engine.odl_accumulate_(Xb, codes, 0.9, As, Bs))
+        t3, _ = timed(lambda: engine.odl_update_dict_(Ds, As, Bs))
         if it > 0:
-            st["encode"].append(t1); st["accumulate"].append(t2); st["update"].append(t3)
-    med = {key: float(np.median(v)) for key, v in st.items()}
-    return sum(med.values()), med
+            st["encode_slice"].append(t1); st["accumulate"].append(t2); st["update"].append(t3)
+    stages = {key: float(np.median(v)) for key, v in st.items()}
+    parity = {"bitwise_reproducible_across_runs": reproducible}
+    if world > 1:
+        allD = torch.empty((world,) + tuple(D.shape), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(allD, D.contiguous())
+        if rank == 0:
+            _, D1, A1 = run(torch.from_numpy(Xfull).to(dev).t(), b, None)                   # ONE GPU, whole minibatches, same order
+            parity.update({"minibatches": n_mb, "max_dD_vs_1gpu": float((D1 - D).abs().max()),
+                           "bitwise_equal_to_1gpu": bool(torch.equal(D1, D) and torch.equal(A1, A)),
+                           "D_identical_across_ranks": bool(all(torch.equal(allD[r], allD[0]) for r in range(world)))})
+        torch.cuda.synchronize(dev); ctx.barrier()
+    return min(ms, ms2), stages, parity
 
 
 def sibling_coders_ms(dev, n=64, K=1024, N=1 << 20, k=5, reps=3):
@@ -485,10 +518,10 @@ def run_own(args):
         except Exception as exc:
             spm_note = "failed: %r" % (exc,)
 
-    odl_ms, odl_stages, odl_note = None, None, None
-    if not args.no_extras and rank == 0:
+    odl_ms, odl_stages, odl_note, odl_parity = -1.0, None, None, None
+    if not args.no_extras:
         try:
-            odl_ms, odl_stages = odl_minibatch_ms(dev)
+            odl_ms, odl_stages, odl_parity = odl_minibatch_ms(dev, rank, world)
         except Exception as exc:
             odl_note = "failed: %r" % (exc,)
 
@@ -499,11 +532,11 @@ def run_own(args):
         except Exception as exc:
             sib_note = "failed: %r" % (exc,)
 
-    t = torch.tensor([ms, e2e_s * 1e3 / e2e_steps, e2e_sparse_s * 1e3 / e2e_steps, ksvd_ms if ksvd_ms is not None else -1.0, spm_ms],
+    t = torch.tensor([ms, e2e_s * 1e3 / e2e_steps, e2e_sparse_s * 1e3 / e2e_steps, ksvd_ms if ksvd_ms is not None else -1.0, spm_ms, odl_ms],
                      dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms, e2e_sparse_ms, ksvd_ms_max, spm_ms_max = [float(v) for v in t.tolist()]
+    ms_max, e2e_ms, e2e_sparse_ms, ksvd_ms_max, spm_ms_max, odl_ms_max = [float(v) for v in t.tolist()]
 
     if rank == 0:
         peaks = {}
@@ -550,8 +583,10 @@ def run_own(args):
                        "scspm_pipeline": {"workload": "BASELINE cfg5: 10000 synthetic 256x256 images sharded by image over %d GPU(s), no collective -> dense SIFT 16x16 / step 6 (1681 descriptors per image) -> Batch-OMP D 128x1024 k=5 -> 3-level max-|z| pooling + l2, images resident on the device, 250 images per call" % world,
                                           "images_per_s": (10000.0 / (spm_ms_max / 1e3)) if spm_ms_max > 0 else None, "ms_total_max_over_ranks": spm_ms_max if spm_ms_max > 0 else None,
                                           "parity_vs_1gpu": spm_parity, "note": spm_note},
-                       "odl_minibatch": {"workload": "ODL minibatch (rank 0 only): 4096 SIFT-like 128-d descriptors, D 128x2048, k=5, beta=0.9: encode -> A,B statistics -> dictionary update",
-                                         "ms_per_minibatch": odl_ms, "stages_ms": odl_stages, "note": odl_note},
+                       "odl_minibatch": {"workload": "BASELINE cfg4: ODL, minibatch 4096 SIFT-like 128-d descriptors split over %d GPU(s), D 128x2048, k=5, beta=0.9, 24 minibatches through online_dict_learn: encode slice -> all-gather (signal, idx, val) -> A,B statistics (fixed order) -> dictionary update (replicated)" % world,
+                                         "ms_per_minibatch": odl_ms_max if odl_ms_max > 0 else None,
+                                         "minibatches_per_s": (1e3 / odl_ms_max) if odl_ms_max > 0 else None,
+                                         "stages_ms_rank0": odl_stages, "parity": odl_parity, "note": odl_note},
                        "sibling_coders": {"workload": "'thresh' / 'iht' coders, 1M synthetic patches (rank 0 only), D 64x1024, k=5, eta=0.2, sparse codes out unless noted",
                                           "ms_per_1M_signals": sib_ms, "note": sib_note}},
         }

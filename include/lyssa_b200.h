@@ -69,6 +69,11 @@ LYS_API int lys_profile_fetch(double* kernel_ms, int64_t* launches, const char**
 /* ---- K1: Gram = D^T D --------------------------------------------------------------
  * replaces `Gram = fast_dot(D.T, D)`, lyssa/sparse_coding.py:630.  G is (K,K) row-major. */
 LYS_API int lys_gram(const float* D, int64_t ldd, int n, int K, float* G, void* stream);
+/* the same with a scratch buffer, which lets it run on the tcgen05 correlation GEMM (n = 64 or 128, K % 256 == 0:
+ * G = D^T D is the correlation of the atoms with the dictionary; 8.6e-8 |d||d| from float64) — what the learners call
+ * once per minibatch / iteration */
+LYS_API size_t lys_gram_workspace_bytes(int n, int K);
+LYS_API int lys_gram_ws(const float* D, int64_t ldd, int n, int K, float* G, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- K2+K3+K4: Batch-OMP encode -------------------------------------------------------
  * replaces `Alpha = fast_dot(D.T, X)` (sparse_coding.py:631) and
@@ -150,6 +155,11 @@ LYS_API int lys_thresh_encode(const float* X, int64_t x_feat_stride, int64_t x_s
                       int32_t* idx, float* val, int32_t* nsel,
                       float* Z, int64_t z_atom_stride, int64_t z_sig_stride,
                       void* workspace, size_t workspace_bytes, void* stream);
+/* The selection alone, on correlations the caller already holds: alpha (N,K) row-major (one signal per row).  Replaces
+ * the bare functions `thresholding(Alpha, ...)` (lyssa/sparse_coding.py:416-425) and `soft_thresholding(Alpha, ...)`
+ * (lyssa/feature_encoding.py:26-37 — the same computation), which take Alpha = D^T X as their argument. */
+LYS_API int lys_topk_select(const float* alpha, int K, int64_t N, int k, int32_t* idx, float* val, int32_t* nsel,
+                    float* Z, int64_t z_atom_stride, int64_t z_sig_stride, void* stream);
 LYS_API size_t lys_iht_workspace_bytes(int n, int K, int64_t N);
 LYS_API int lys_iht_encode(const float* X, int64_t x_feat_stride, int64_t x_sig_stride,
                    const float* D, int64_t ldd, int n, int K, int64_t N, int k, float eta, int n_iter,
@@ -219,6 +229,20 @@ LYS_API int lys_approx_ksvd_sweep(float* R, float* D, int64_t ldd,
                           int32_t* unused, void* comm,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- exact K-SVD sweep ------------------------------------------
+ * replaces the atom loop of ksvd(), lyssa/dict_learning/ksvd.py:19-43: per atom, (d, x) <- top singular triplet of
+ * R_k = R[:,users] + d x (:36-39; the reference calls scikit-learn's randomized_svd(R_k, 1, n_iter=10)), then
+ * R[:,users] = R_k - d x (:41).  Same in-place contract, CSR and residual as lys_approx_ksvd_sweep.  The triplet comes
+ * from the n x n Gram matrix R_k R_k^T (one integer all-reduce per atom, then a replicated eigen-solve, ksvd_exact.cu):
+ * d is the top left singular vector to ~1e-6 wherever the two largest singular values differ by more than 0.4 %,
+ * with the sign that keeps d.d_old >= 0 (the reference's sign is arbitrary).  n <= 64; single GPU (comm is not taken:
+ * the per-atom payload is n(n+1)/2 words); other n return LYS_EUNSUPPORTED. */
+LYS_API size_t lys_ksvd_exact_workspace_bytes(int n, int K);
+LYS_API int lys_ksvd_exact_sweep(float* R, float* D, int64_t ldd, float* val,
+                         const int32_t* rowptr, const int32_t* entries,
+                         int n, int K, int64_t N, int k, int n_cycles,
+                         int32_t* unused, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- K8 / K14 helpers -------------------------------------------------------------------
  * norm_cols: D[:,c] /= (||D[:,c]||_2 + eps), lyssa/utils/math.py:65-71 (eps = 2^-52).
  * gather_cols: D[:,j] = X[:, cols[j]], the device half of init_dictionary
@@ -230,13 +254,16 @@ LYS_API int lys_gather_cols(const float* X, int64_t x_feat_stride, int64_t x_sig
 
 /* ---- K12/K13: online dictionary learning ------------------------------------------------
  * accumulate: A = beta*A + Z_b Z_b^T, B = beta*B + X_b Z_b^T from sparse codes
- * (lyssa/dict_learning/online_dict_learn.py:84-85).  A (K,K), B (n,K) row-major.
- * With `scale_only` != 0 only the beta scaling is applied (used before a multi-rank sum).
+ * (lyssa/dict_learning/online_dict_learn.py:84-85).  A (K,K), B (n,K) row-major.  Every sum runs in a fixed order
+ * (users of an atom ascending), so A and B are bitwise reproducible and identical on every rank that is given the
+ * same minibatch — the multi-GPU learner all-gathers the minibatch's codes and signals and accumulates redundantly
+ * instead of all-reducing the K x K statistics.  beta == 0 writes the sums alone.
  * update: D <- norm_cols(clamp(D + (B - D A) diag(1/(A_kk + eps)))), :91-98 (Jacobi, stale
  * D A; clamp only if non_neg). */
+LYS_API size_t lys_odl_accumulate_workspace_bytes(int K, int64_t b, int k);
 LYS_API int lys_odl_accumulate(const float* Xb, int64_t x_feat_stride, int64_t x_sig_stride,
                        const int32_t* idx, const float* val, int n, int K, int64_t b, int k,
-                       float beta, float* A, float* B, void* stream);
+                       float beta, float* A, float* B, void* workspace, size_t workspace_bytes, void* stream);
 LYS_API size_t lys_odl_update_workspace_bytes(int n, int K);
 LYS_API int lys_odl_update_dict(float* D, int64_t ldd, const float* A, const float* B, int n, int K,
                         int non_neg, void* workspace, size_t workspace_bytes, void* stream);

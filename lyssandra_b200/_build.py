@@ -15,7 +15,7 @@ CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "liblyssa_b200.so")
 _STAMP = os.path.join(_PKG, "csrc", ".build_stamp")
 
-SOURCES = ["runtime.cu", "gemm.cu", "bomp_generic.cu", "bomp_fast.cu", "corr_gemm_tc.cu", "bomp_fused.cu", "bomp.cu", "ksvd.cu", "ksvd_sweep.cu", "odl.cu", "comm.cu", "spm.cu", "dsift.cu", "thresh.cu"]
+SOURCES = ["runtime.cu", "gemm.cu", "bomp_generic.cu", "bomp_fast.cu", "corr_gemm_tc.cu", "bomp_fused.cu", "bomp.cu", "ksvd.cu", "ksvd_sweep.cu", "ksvd_exact.cu", "odl.cu", "odl_gemm_tc.cu", "comm.cu", "spm.cu", "dsift.cu", "thresh.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--threads", "0"]
 

@@ -25,6 +25,8 @@ SIGNATURES = {
     "lys_profile_enable": (c_int, [c_int]),
     "lys_profile_fetch": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_i64), ctypes.POINTER(ctypes.c_char_p), c_int]),
     "lys_gram": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
+    "lys_gram_workspace_bytes": (c_sz, [c_int, c_int]),
+    "lys_gram_ws": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
     "lys_bomp_workspace_bytes": (c_sz, [c_int, c_int, c_i64, c_int]),
     "lys_bomp_encode": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_i64, c_int,
                                 c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_sz, c_vp]),
@@ -33,6 +35,7 @@ SIGNATURES = {
     "lys_omp_workspace_bytes": (c_sz, [c_int, c_int, c_i64, c_int]),
     "lys_omp_encode": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_i64, c_int, c_f, c_int,
                                c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp]),
+    "lys_topk_select": (c_int, [c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "lys_thresh_workspace_bytes": (c_sz, [c_int, c_int, c_i64]),
     "lys_thresh_encode": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_i64, c_int,
                                   c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_sz, c_vp]),
@@ -51,9 +54,12 @@ SIGNATURES = {
     "lys_ksvd_sweep_workspace_bytes": (c_sz, [c_int, c_int, c_i64, c_int]),
     "lys_approx_ksvd_sweep": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int,
                                       c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "lys_ksvd_exact_workspace_bytes": (c_sz, [c_int, c_int]),
+    "lys_ksvd_exact_sweep": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
     "lys_norm_cols": (c_int, [c_vp, c_i64, c_int, c_int, c_vp]),
     "lys_gather_cols": (c_int, [c_vp, c_i64, c_i64, c_int, c_vp, c_int, c_vp, c_i64, c_vp, c_vp]),
-    "lys_odl_accumulate": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_f, c_vp, c_vp, c_vp]),
+    "lys_odl_accumulate_workspace_bytes": (c_sz, [c_int, c_i64, c_int]),
+    "lys_odl_accumulate": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_f, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "lys_odl_update_workspace_bytes": (c_sz, [c_int, c_int]),
     "lys_odl_update_dict": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_sz, c_vp]),
     "lys_frobenius2": (c_int, [c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),

@@ -161,6 +161,34 @@ int sgemm_strided(const float* A, int64_t sai, int64_t sap,
 
 }  // namespace lys
 
+namespace lys {
+bool corr_gemm_tc_supported(int n, int K);
+size_t corr_gemm_tc_planes_bytes(int n, int K);
+int corr_gemm_tc_prepare(const float* D, int64_t ldd, int n, int K, void* planes, cudaStream_t stream);
+int corr_gemm_tc(const float* X, int64_t xfs, int64_t xss, const void* planes,
+                 int n, int K, int64_t C, float* alpha, cudaStream_t stream);
+}
+
+extern "C" size_t lys_gram_workspace_bytes(int n, int K)
+{
+    return lys::corr_gemm_tc_supported(n, K) ? lys::align_up(lys::corr_gemm_tc_planes_bytes(n, K), 256) : 0;
+}
+
+// Gram with a scratch buffer: on the tcgen05 correlation GEMM where its shapes allow (n = 64 or 128, K a multiple of
+// 256: G = D^T D is the correlation of the atoms with the dictionary), else the fp32 SIMT GEMM of lys_gram
+extern "C" int lys_gram_ws(const float* D, int64_t ldd, int n, int K, float* G, void* workspace, size_t workspace_bytes, void* stream)
+{
+    LYS_CHECK_ARG(D && G, "lys_gram_ws: null pointer");
+    LYS_CHECK_ARG(n >= 1 && n <= LYS_MAX_FEATURES && K >= 1 && K <= LYS_MAX_ATOMS && ldd >= K,
+                  "lys_gram_ws: bad shape n=%d K=%d ldd=%lld", n, K, (long long)ldd);
+    if (lys::corr_gemm_tc_supported(n, K) && workspace && workspace_bytes >= lys_gram_workspace_bytes(n, K)) {
+        int rc = lys::corr_gemm_tc_prepare(D, ldd, n, K, workspace, (cudaStream_t)stream);
+        if (rc) return rc;
+        return lys::corr_gemm_tc(D, ldd, 1, workspace, n, K, K, G, (cudaStream_t)stream);      // "signals" = the atoms themselves
+    }
+    return lys::sgemm_strided(D, 1, ldd, D, ldd, 1, G, K, 1, K, K, n, (cudaStream_t)stream);
+}
+
 extern "C" int lys_gram(const float* D, int64_t ldd, int n, int K, float* G, void* stream)
 {
     LYS_CHECK_ARG(D && G, "lys_gram: null pointer");

@@ -31,34 +31,12 @@
 // Multi-rank: one warp of every CTA forwards the completed local sums of "its" atoms (atom c -> CTA c mod grid)
 // into every peer's mailbox as tagged 8-byte words (comm.cuh); readers add the peers' words to their own sum.
 #include "comm.cuh"
+#include "sweep_common.cuh"
 #include <algorithm>
 #include <cmath>
 
 namespace lys {
 namespace {
-
-using u64 = unsigned long long;
-
-__device__ __forceinline__ u64 ld_relaxed_gpu(const u64* p)
-{
-    u64 v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ u64 ld_relaxed_sys(const u64* p)
-{
-    u64 v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_sys(u64* p, u64 v)
-{
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ void red_add(u64* p, u64 v)
-{
-    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 
 // bounds[c][b] = first CSR position of atom c whose signal is >= b*S   (b = 0..G), bounds[c][G] = rowptr[c+1]
 __global__ void sweep_bounds_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ entries,
@@ -128,14 +106,6 @@ __global__ void sweep_scale_kernel(const double* __restrict__ fro /* ||R||^2, ||
     }
 }
 
-// entry id -> signal index: ent / k by multiply-shift (k <= 32, ent < 2^31; M = ceil(2^(32+s)/k) is exact
-// for every 32-bit numerator because M*k - 2^(32+s) < k <= 2^s)
-struct FastDiv { unsigned long long M; int s; };
-__device__ __forceinline__ int fdiv(int ent, FastDiv d)
-{
-    return (int)(((unsigned long long)(unsigned)ent * d.M) >> (32 + d.s));
-}
-
 // 16 warps per CTA (one CTA per SM, 128 registers per thread).  Multi-rank: warp 15 forwards, 15 warps compute.
 constexpr int SW_THREADS = 512;
 template <int CW> __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CW * 32) : "memory"); }
@@ -168,24 +138,132 @@ __device__ __forceinline__ Range make_range(int lo, int hi, int warp, int U)
     return r;
 }
 
-// ids, coefficients, links of a warp's users + an L2 prefetch of their residual rows.  Issued two atoms ahead: an atom's
-// coefficients are only written by that atom's own phase 2, and the linked coefficient (atom c-1 in the same signal) is
-// read before phase 2 of c-1 of THIS sweep can have run only if ... it has not: the set of atom c+2 is loaded during
-// iteration c, phase 2 of atom c+1 runs in iteration c+1.
-__device__ __forceinline__ UserSet load_set(const SweepArgs& a, const Range& rg, int lane)
+// ids, coefficients and links of a warp's users, fetched in three dependent stages that run in three consecutive
+// iterations of the atom loop (each stage's loads are consumed an iteration later, so none of the three L2 round trips
+// of the chain entries -> {val, link} -> linked val sits on the per-atom critical path):
+//   stage 1 (4 atoms ahead): ent            stage 2 (3 ahead): x = val[ent], lk = link[ent], L2 prefetch of the row
+//   stage 3 (2 ahead): xp = val of the previous atom in the same signal (read before that atom's own phase 2 runs:
+//   the set of atom c+2 is completed during iteration c, phase 2 of atom c+1 runs in iteration c+1)
+__device__ __forceinline__ int set_stage1(const SweepArgs& a, const Range& rg, int lane)
 {
-    UserSet s;
-    s.ent = -1; s.x = 0.f; s.lk = 255; s.xp = 0.f;
-    if (lane < rg.nu) {
-        s.ent = __ldg(a.entries + rg.p0 + lane);
-        s.x = __ldcg(a.val + s.ent);
-        s.lk = __ldg(a.link + s.ent);
-        const int i = fdiv(s.ent, a.kdiv);
-        if (s.lk != 255) s.xp = __ldcg(a.val + (int64_t)i * a.k + s.lk);
-        const char* row = reinterpret_cast<const char*>(a.R + (int64_t)i * a.n);
+    return (lane < rg.nu) ? __ldg(a.entries + rg.p0 + lane) : -1;
+}
+__device__ __forceinline__ void set_stage2(const SweepArgs& a, int ent, float& x, int& lk)
+{
+    x = 0.f; lk = 255;
+    if (ent >= 0) {
+        x = __ldcg(a.val + ent);
+        lk = __ldg(a.link + ent);
+        const char* row = reinterpret_cast<const char*>(a.R + (int64_t)fdiv(ent, a.kdiv) * a.n);
         for (int off = 0; off < a.n * 4; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off));
     }
+}
+__device__ __forceinline__ float set_stage3(const SweepArgs& a, int ent, int lk)
+{
+    return (ent >= 0 && lk != 255) ? __ldcg(a.val + (int64_t)fdiv(ent, a.kdiv) * a.k + lk) : 0.f;
+}
+__device__ __forceinline__ UserSet load_set(const SweepArgs& a, const Range& rg, int lane)      // all stages at once (prologue)
+{
+    UserSet s;
+    s.ent = set_stage1(a, rg, lane);
+    set_stage2(a, s.ent, s.x, s.lk);
+    s.xp = set_stage3(a, s.ent, s.lk);
     return s;
+}
+
+// Sum each of the CNT values v[0..CNT) over the 32 lanes with CNT-1 + log2(32/CNT) shuffles instead of 5 CNT: at every
+// level the two halves of the value list are exchanged between lane l and lane l ^ OFF.  Returns the total of ONE
+// value per lane: value index = multi_owner<U>(lane).
+template <int CNT, int OFF>
+__device__ __forceinline__ float multi_reduce(float (&v)[CNT], int lane)
+{
+    if constexpr (OFF == 0) {
+        return v[0];
+    } else if constexpr (CNT > 1) {
+        constexpr int H = CNT / 2;
+        float w[H];
+        const bool upper = (lane & OFF) != 0;
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            const float send = upper ? v[j] : v[j + H];
+            const float keep = upper ? v[j + H] : v[j];
+            w[j] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+        }
+        return multi_reduce<H, OFF / 2>(w, lane);
+    } else {
+        float w[1] = {v[0] + __shfl_xor_sync(0xffffffffu, v[0], OFF)};
+        return multi_reduce<1, OFF / 2>(w, lane);
+    }
+}
+template <int U> __device__ __forceinline__ int multi_owner(int lane)          // which value a lane ends up with
+{
+    int u = 0, off = 16;
+#pragma unroll
+    for (int h = U / 2; h >= 1; h >>= 1, off >>= 1) u += (lane & off) ? h : 0;
+    return u;
+}
+template <int U> __host__ __device__ constexpr int multi_lane(int u)           // lowest lane that holds value u
+{
+    int l = 0, off = 16;
+    for (int h = U / 2; h >= 1; h >>= 1, off >>= 1) if (u & h) l |= off;
+    return l;
+}
+
+// LYS_ROWMAP = 1: a lane owns NPL consecutive features and moves a row with one 4*NPL-byte access.  Measured SLOWER on the
+// same box (6.8 vs 5.9 ms per cfg3 sweep: the stride-NPL feature index costs bank conflicts in the reduction arrays
+// and the wider accesses buy nothing on 256-byte rows), so the default is features strided by 32 over the lanes.
+#ifndef LYS_ROWMAP
+#define LYS_ROWMAP 0
+#endif
+#if LYS_ROWMAP
+#define LYS_FEAT(lane, q) ((lane) * NPL + (q))
+#else
+#define LYS_FEAT(lane, q) ((lane) + 32 * (q))
+#endif
+// A lane owns the NPL consecutive features [lane*NPL, lane*NPL + NPL) of a row, so a residual row moves with ONE
+// 4*NPL-byte access per lane (a 256-byte row = one LDG.64 / STG.64 per warp at n = 64) whenever n is a multiple of NPL
+// (rows are then 4*NPL-byte aligned: R is 16-byte aligned and the row stride is n floats).
+template <int NPL>
+__device__ __forceinline__ void load_row(const float* __restrict__ r, int n, int lane, float (&v)[NPL])
+{
+    const int f0 = lane * NPL;
+    if (LYS_ROWMAP && (n % NPL) == 0) {
+        if (f0 < n) {
+            if constexpr (NPL == 1) v[0] = __ldcg(r + f0);
+            else if constexpr (NPL == 2) { const float2 t = __ldcg(reinterpret_cast<const float2*>(r + f0)); v[0] = t.x; v[1] = t.y; }
+            else {
+#pragma unroll
+                for (int q = 0; q < NPL; q += 4) {
+                    const float4 t = __ldcg(reinterpret_cast<const float4*>(r + f0 + q));
+                    v[q] = t.x; v[q + 1] = t.y; v[q + 2] = t.z; v[q + 3] = t.w;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) v[q] = 0.f;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) { const int f = LYS_FEAT(lane, q); v[q] = (f < n) ? __ldcg(r + f) : 0.f; }
+    }
+}
+template <int NPL>
+__device__ __forceinline__ void store_row(float* __restrict__ r, int n, int lane, const float (&v)[NPL])
+{
+    const int f0 = lane * NPL;
+    if (LYS_ROWMAP && (n % NPL) == 0) {
+        if (f0 < n) {
+            if constexpr (NPL == 1) __stcg(r + f0, v[0]);
+            else if constexpr (NPL == 2) __stcg(reinterpret_cast<float2*>(r + f0), make_float2(v[0], v[1]));
+            else {
+#pragma unroll
+                for (int q = 0; q < NPL; q += 4) __stcg(reinterpret_cast<float4*>(r + f0 + q), make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]));
+            }
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) { const int f = LYS_FEAT(lane, q); if (f < n) __stcg(r + f, v[q]); }
+    }
 }
 
 template <int NPL, int U>
@@ -196,11 +274,7 @@ __device__ __forceinline__ void load_rows(const SweepArgs& a, const UserSet& s, 
         const int e = __shfl_sync(0xffffffffu, s.ent, u);
 #pragma unroll
         for (int q = 0; q < NPL; ++q) rv[u][q] = 0.f;
-        if (u < nu) {
-            const float* r = a.R + (int64_t)fdiv(e, a.kdiv) * a.n;
-#pragma unroll
-            for (int q = 0; q < NPL; ++q) { const int f = lane + 32 * q; if (f < a.n) rv[u][q] = __ldcg(r + f); }
-        }
+        if (u < nu) load_row<NPL>(a.R + (int64_t)fdiv(e, a.kdiv) * a.n, a.n, lane, rv[u]);
     }
 }
 
@@ -236,7 +310,7 @@ __device__ __forceinline__ void publish_atom(const SweepArgs& a, int c, const Us
         const float* r = a.R + (int64_t)i * n;
 #pragma unroll
         for (int q = 0; q < NPL; ++q) {
-            const int f = lane + 32 * q;
+            const int f = LYS_FEAT(lane, q);
             const float rvv = (f < n) ? __ldcg(r + f) : 0.f;
             S[q] = fmaf(rvv, xo, S[q]);
             if (lk != 255) T[q] = fmaf(rvv, xo, T[q]);
@@ -251,7 +325,7 @@ __device__ __forceinline__ void publish_atom(const SweepArgs& a, int c, const Us
     float* mine = red + warp * lda;
 #pragma unroll
     for (int q = 0; q < NPL; ++q) {
-        const int f = lane + 32 * q;
+        const int f = LYS_FEAT(lane, q);
         if (f < n) { mine[f] = S[q]; mine[n + f] = T[q]; }
     }
     if (lane == 0) { mine[2 * n] = aa; mine[2 * n + 1] = xx; }
@@ -269,6 +343,14 @@ __device__ __forceinline__ void publish_atom(const SweepArgs& a, int c, const Us
         red_add(a.acc + ((size_t)c * lda + t) * a.acc_stride, ((u64)q << 8) + 1ull);
     }
 }
+
+#ifdef LYS_BRINGUP
+// bring-up: cycles per phase of the atom loop, CTA gridDim.x/2, thread 0 (scripts/sweep_phases.py)
+__device__ unsigned long long g_sweep_timing[8];
+#define LYS_SW_LAP(i) do { if (b == (int)gridDim.x / 2 && tid == 0) { const long long now_ = clock64(); g_sweep_timing[i] += (unsigned long long)(now_ - t_lap); t_lap = now_; } } while (0)
+#else
+#define LYS_SW_LAP(i) do { } while (0)
+#endif
 
 template <int NPL, bool MULTI>
 __global__ void __launch_bounds__(SW_THREADS, 1)
@@ -317,10 +399,18 @@ ksvd_sweep_kernel(const SweepArgs a)
     Range rgC = make_range<CW>(lo, hi, warp, U);
     bound_of(1, lo, hi);
     Range rgN = make_range<CW>(lo, hi, warp, U);
-    int lo2, hi2;
+    // the pipeline of user sets: atom c+2 (ids, coefficients, links known), c+3 (ids known), c+4 (bounds known)
+    int lo2, hi2, lo3, hi3, lo4, hi4;
     bound_of(2, lo2, hi2);
+    bound_of(3, lo3, hi3);
+    bound_of(4, lo4, hi4);
     UserSet setC = load_set(a, rgC, lane);
     UserSet setN = load_set(a, rgN, lane);
+    UserSet set2;
+    set2.ent = set_stage1(a, make_range<CW>(lo2, hi2, warp, U), lane);
+    set_stage2(a, set2.ent, set2.x, set2.lk);
+    set2.xp = 0.f;
+    int ent3 = set_stage1(a, make_range<CW>(lo3, hi3, warp, U), lane);
     float rvC[U][NPL], rvN[U][NPL];
     load_rows<NPL, U>(a, setC, rgC.nu, lane, rvC);
     publish_atom<NPL, U, CW>(a, 0, setC, rgC, rvC, red, fx, tid, lane, warp);
@@ -330,13 +420,19 @@ ksvd_sweep_kernel(const SweepArgs a)
     float gP = 0.f;
 #pragma unroll
     for (int q = 0; q < NPL; ++q) {
-        const int f = lane + 32 * q;
+        const int f = LYS_FEAT(lane, q);
         dold[q] = (f < n) ? __ldg(a.Dt + f) : 0.f;
         dnP[q] = 0.f; doldP[q] = 0.f; doldN[q] = 0.f;
     }
+    const int my_user = multi_owner<U>(lane);
 
+#ifdef LYS_BRINGUP
+    long long t_lap = clock64();
+#endif
     for (int c = 0; c < K; ++c) {
         if (tid == 0) *reinterpret_cast<volatile int*>(&s_progress) = c;
+        // ---- rows of the look-ahead atom c+1 first: their latency covers everything up to the sums below
+        if (c + 1 < K) load_rows<NPL, U>(a, setN, rgN.nu, lane, rvN);
         // ---- rows of atom c that atom c-1 has just rewritten (its users were loaded before that update)
         {
             const unsigned stale = __ballot_sync(0xffffffffu, lane < rgC.nu && setC.lk != 255);
@@ -345,24 +441,27 @@ ksvd_sweep_kernel(const SweepArgs a)
                 for (int u = 0; u < U; ++u) {
                     if ((stale >> u) & 1u) {
                         const int e = __shfl_sync(0xffffffffu, setC.ent, u);
-                        const float* r = a.R + (int64_t)fdiv(e, a.kdiv) * n;
-#pragma unroll
-                        for (int q = 0; q < NPL; ++q) { const int f = lane + 32 * q; if (f < n) rvC[u][q] = __ldcg(r + f); }
+                        load_row<NPL>(a.R + (int64_t)fdiv(e, a.kdiv) * n, n, lane, rvC[u]);
                     }
                 }
             }
         }
-        // ---- two atoms ahead: ids / coefficients / links + L2 prefetch of the rows; three ahead: CSR bounds
-        const Range rgP = make_range<CW>(lo2, hi2, warp, U);
-        const UserSet setP = load_set(a, rgP, lane);
-        bound_of(c + 3, lo2, hi2);
+        // ---- the three stages of the sets of atoms c+2, c+3, c+4 (consumed at the end of this iteration) and the
+        //      CSR bounds of atom c+5
+        const float xp2 = set_stage3(a, set2.ent, set2.lk);
+        float x3; int lk3;
+        set_stage2(a, ent3, x3, lk3);
+        const int ent4 = set_stage1(a, make_range<CW>(lo4, hi4, warp, U), lane);
+        int lo5, hi5;
+        bound_of(c + 5, lo5, hi5);
+        LYS_SW_LAP(0);
         if (c + 1 < K) {
 #pragma unroll
-            for (int q = 0; q < NPL; ++q) { const int f = lane + 32 * q; doldN[q] = (f < n) ? __ldg(a.Dt + (size_t)(c + 1) * n + f) : 0.f; }
+            for (int q = 0; q < NPL; ++q) { const int f = LYS_FEAT(lane, q); doldN[q] = (f < n) ? __ldg(a.Dt + (size_t)(c + 1) * n + f) : 0.f; }
             // ---- look-ahead: sums of atom c+1 over the rows as they are before atom c is applied
-            load_rows<NPL, U>(a, setN, rgN.nu, lane, rvN);
             publish_atom<NPL, U, CW>(a, c + 1, setN, rgN, rvN, red, fx, tid, lane, warp);
         }
+        LYS_SW_LAP(1);
         // ---- reduced sums of atom c (published one iteration ago)
         for (int t = tid; t < lda; t += CW * 32) {
             const u64* w = a.acc + ((size_t)c * lda + t) * a.acc_stride;
@@ -385,7 +484,9 @@ ksvd_sweep_kernel(const SweepArgs a)
             const double scale = (t < 2 * n + 2) ? (MULTI ? 256.0 : 1.0) / fx : (MULTI ? 1.0 : 1.0 / 256.0);
             svec[t] = (float)((double)q * scale);
         }
+        LYS_SW_LAP(2);
         compute_sync<CW>();
+        LYS_SW_LAP(3);
         // ---- new atom (every warp computes it redundantly: no second barrier)          (ksvd.py:118-119)
         const float aa = svec[2 * n], sxx = svec[2 * n + 1];
         const bool used = svec[2 * n + 2] != 0.f;                     // uniform over CTAs and ranks
@@ -393,56 +494,68 @@ ksvd_sweep_kernel(const SweepArgs a)
         float dT = 0.f;
 #pragma unroll
         for (int q = 0; q < NPL; ++q) {
-            const int f = lane + 32 * q;
+            const int f = LYS_FEAT(lane, q);
             sv[q] = (f < n) ? svec[f] : 0.f;
             tv[q] = (f < n) ? svec[n + f] : 0.f;
             dT = fmaf(dnP[q], tv[q], dT);
         }
         dT = warp_sum(dT);
         const float coef = fmaf(gP, aa, dT);                          // sum over shared users of x'_{c-1,i} x_{c,i}
-        float dsq = 0.f;
+        float dsq = 0.f, dsv = 0.f;
 #pragma unroll
         for (int q = 0; q < NPL; ++q) {
             sv[q] = fmaf(dold[q], sxx, fmaf(-dnP[q], coef, fmaf(doldP[q], aa, sv[q])));      // R_k x = R x + d (x.x)
             dsq = fmaf(sv[q], sv[q], dsq);
+            dsv = fmaf(dold[q], sv[q], dsv);
         }
-        dsq = warp_sum(dsq);
+        {   // ||s||^2 and d.s in one exchange: lanes < 16 carry one sum, lanes >= 16 the other
+            float two[2] = {dsq, dsv};
+            const float mine = multi_reduce<2, 16>(two, lane);
+            dsq = __shfl_sync(0xffffffffu, mine, 0);
+            dsv = __shfl_sync(0xffffffffu, mine, 16);
+        }
         const float inv = 1.f / (sqrtf(dsq) + kRefEps);              // utils/math.py:61-62
         float g = 0.f;
 #pragma unroll
         for (int q = 0; q < NPL; ++q) {
             dn[q] = used ? sv[q] * inv : dold[q];                    // an atom nobody uses is left alone (:112-115)
-            g = fmaf(dold[q], dn[q], g);
+            g = fmaf(dold[q], dold[q], g);
         }
-        g = warp_sum(g);
+        g = used ? dsv * inv : warp_sum(g);                          // g = d.d'
         if (b == 0 && warp == 0) {
 #pragma unroll
-            for (int q = 0; q < NPL; ++q) { const int f = lane + 32 * q; if (f < n) a.Dt_new[(size_t)c * n + f] = dn[q]; }
+            for (int q = 0; q < NPL; ++q) { const int f = LYS_FEAT(lane, q); if (f < n) a.Dt_new[(size_t)c * n + f] = dn[q]; }
             if (!used && lane == 0) a.unused[c] = 1;
         }
+        LYS_SW_LAP(4);
         // ---- phase 2: x' = R_k^T d' ; R <- R_k - d' x'                                  (ksvd.py:121-123)
         if (used) {
-            float xnew = 0.f;
+            // all dot products of the warp's users in one multi-value reduction; lane multi_lane(u) then owns user u
+            float dots[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                float d = 0.f;
+#pragma unroll
+                for (int q = 0; q < NPL; ++q) d = fmaf(rvC[u][q], dn[q], d);
+                dots[u] = d;
+            }
+            const float dot_mine = multi_reduce<U, 16>(dots, lane);
+            const float x_mine = __shfl_sync(0xffffffffu, setC.x, my_user);
+            const int ent_mine = __shfl_sync(0xffffffffu, setC.ent, my_user);
+            const float xn_mine = fmaf(x_mine, g, dot_mine);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const float x = __shfl_sync(0xffffffffu, setC.x, u);
                 const int e = __shfl_sync(0xffffffffu, setC.ent, u);
+                const float xn = __shfl_sync(0xffffffffu, xn_mine, multi_lane<U>(u));
                 if (u < rgC.nu) {
-                    float dot = 0.f;
+                    float o[NPL];
 #pragma unroll
-                    for (int q = 0; q < NPL; ++q) dot = fmaf(rvC[u][q], dn[q], dot);
-                    dot = warp_sum(dot);
-                    const float xn = fmaf(x, g, dot);
-                    float* r = a.R + (int64_t)fdiv(e, a.kdiv) * n;
-#pragma unroll
-                    for (int q = 0; q < NPL; ++q) {
-                        const int f = lane + 32 * q;
-                        if (f < n) __stcg(r + f, fmaf(-dn[q], xn, fmaf(dold[q], x, rvC[u][q])));
-                    }
-                    if (lane == u) xnew = xn;
+                    for (int q = 0; q < NPL; ++q) o[q] = fmaf(-dn[q], xn, fmaf(dold[q], x, rvC[u][q]));
+                    store_row<NPL>(a.R + (int64_t)fdiv(e, a.kdiv) * n, n, lane, o);
                 }
             }
-            if (lane < rgC.nu) __stcg(a.val + setC.ent, xnew);
+            if (my_user < rgC.nu && (lane & (32 / U - 1)) == 0) __stcg(a.val + ent_mine, xn_mine);
             for (int p = rgC.ovf + warp; p < rgC.hi; p += CW) {
                 const int e = __ldg(a.entries + p);
                 const float xo = __ldcg(a.val + e);
@@ -450,7 +563,7 @@ ksvd_sweep_kernel(const SweepArgs a)
                 float r2[NPL], dot = 0.f;
 #pragma unroll
                 for (int q = 0; q < NPL; ++q) {
-                    const int f = lane + 32 * q;
+                    const int f = LYS_FEAT(lane, q);
                     r2[q] = (f < n) ? __ldcg(r + f) : 0.f;
                     dot = fmaf(r2[q], dn[q], dot);
                 }
@@ -458,14 +571,16 @@ ksvd_sweep_kernel(const SweepArgs a)
                 const float xn = fmaf(xo, g, dot);
 #pragma unroll
                 for (int q = 0; q < NPL; ++q) {
-                    const int f = lane + 32 * q;
+                    const int f = LYS_FEAT(lane, q);
                     if (f < n) __stcg(r + f, fmaf(-dn[q], xn, fmaf(dold[q], xo, r2[q])));
                 }
                 if (lane == 0) __stcg(a.val + e, xn);
             }
         }
+        LYS_SW_LAP(5);
         // rows / coefficients of this CTA's signals are re-read by other warps of THIS CTA only
         compute_sync<CW>();
+        LYS_SW_LAP(6);
         // ---- rotate the pipeline
         gP = g;
 #pragma unroll
@@ -475,7 +590,10 @@ ksvd_sweep_kernel(const SweepArgs a)
 #pragma unroll
             for (int q = 0; q < NPL; ++q) rvC[u][q] = rvN[u][q];
         setC = setN; rgC = rgN;
-        setN = setP; rgN = rgP;
+        setN = set2; setN.xp = xp2; rgN = make_range<CW>(lo2, hi2, warp, U);
+        set2.ent = ent3; set2.x = x3; set2.lk = lk3;
+        ent3 = ent4;
+        lo2 = lo3; hi2 = hi3; lo3 = lo4; hi3 = hi4; lo4 = lo5; hi4 = hi5;
     }
 }
 
@@ -505,6 +623,18 @@ int sweep_lda(int n) { return (2 * n + 3 + 3) / 4 * 4; }
 int sweep_acc_stride(int n, int K) { return ((size_t)K * sweep_lda(n) * 32 <= (64u << 20)) ? 4 : 1; }
 
 }  // namespace
+
+int sweep_grid_size() { return sweep_grid(); }
+
+int sweep_bounds(const int32_t* rowptr, const int32_t* entries, int K, int k, int grid, int64_t N, int32_t* bounds, cudaStream_t stream)
+{
+    const int64_t S = std::max<int64_t>(1, (N + grid - 1) / grid);
+    const int items = K * (grid + 1);
+    sweep_bounds_kernel<<<(items + 255) / 256, 256, 0, stream>>>(rowptr, entries, K, k, grid, S, bounds);
+    LYS_LAUNCH_CHECK("sweep_bounds_kernel");
+    return LYS_OK;
+}
+
 }  // namespace lys
 
 using namespace lys;
@@ -565,10 +695,7 @@ extern "C" int lys_approx_ksvd_sweep(float* R, float* D, int64_t ldd, const int3
     LYS_CUDA(cudaMemsetAsync(unused, 0, sizeof(int32_t) * (size_t)K, stream));
     int rc = transpose(D, ldd, w.Dt, n, n, K, stream);
     if (rc) return rc;
-    const int64_t S = std::max<int64_t>(1, (N + grid - 1) / grid);
-    const int items = K * (grid + 1);
-    sweep_bounds_kernel<<<(items + 255) / 256, 256, 0, stream>>>(rowptr, entries, K, k, grid, S, w.bounds);
-    LYS_LAUNCH_CHECK("sweep_bounds_kernel");
+    if ((rc = sweep_bounds(rowptr, entries, K, k, grid, N, w.bounds, stream))) return rc;
     if (N > 0) {
         sweep_link_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(idx, val, N, k, w.link);
         LYS_LAUNCH_CHECK("sweep_link_kernel");
@@ -579,9 +706,7 @@ extern "C" int lys_approx_ksvd_sweep(float* R, float* D, int64_t ldd, const int3
     a.entries = entries; a.link = w.link; a.bounds = w.bounds;
     a.n = n; a.K = K; a.k = k; a.lda = sweep_lda(n); a.acc_stride = sweep_acc_stride(n, K);
     a.unused = unused; a.acc = w.acc; a.fx = w.fx; a.pc = pc;
-    a.kdiv.s = 0;
-    while ((1 << a.kdiv.s) < k) ++a.kdiv.s;
-    a.kdiv.M = ((1ull << (32 + a.kdiv.s)) + (unsigned long long)k - 1) / (unsigned long long)k;
+    a.kdiv = make_fastdiv(k);
 
     for (int cyc = 0; cyc < n_cycles; ++cyc) {
         // fixed-point scale from the norms of the residual and of the coefficients as they are now
@@ -607,3 +732,14 @@ extern "C" int lys_approx_ksvd_sweep(float* R, float* D, int64_t ldd, const int3
     }
     return transpose(w.Dt, n, D, ldd, K, n, stream);
 }
+
+#ifdef LYS_BRINGUP
+extern "C" __attribute__((visibility("default"))) int lys_debug_sweep_timing(unsigned long long* out8)
+{
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out8, lys::g_sweep_timing, sizeof(unsigned long long) * 8) != cudaSuccess) return -2;
+    unsigned long long zero[8] = {0};
+    if (cudaMemcpyToSymbol(lys::g_sweep_timing, zero, sizeof(zero)) != cudaSuccess) return -2;
+    return 0;
+}
+#endif

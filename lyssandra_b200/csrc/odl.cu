@@ -10,48 +10,144 @@
 #include <algorithm>
 
 namespace lys {
+
+int da_gemm_tc_splits(int K);
+bool da_gemm_tc_supported(int n, int K);
+int da_gemm_tc(const float* D, int64_t ldd, const float* A, int n, int K, float* partial, cudaStream_t stream);
+
 namespace {
 
-__global__ void scale_kernel(float* __restrict__ p, int64_t count, float beta)
+// ---- users-of-atom lists of one minibatch, ONE CTA (b*k is a few 10^4 entries): histogram, scan and fill in shared
+// memory.  The order inside a list is whatever the atomics produce; the consumer sorts every list (a handful of
+// entries) before it accumulates, so the statistics do not depend on it.
+__global__ void __launch_bounds__(1024)
+odl_csr_kernel(const int32_t* __restrict__ idx, const float* __restrict__ val, int64_t E, int K,
+               int32_t* __restrict__ rowptr /* K+1 */, int32_t* __restrict__ entries /* E */)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < count; i += stride) p[i] *= beta;
-}
-
-// one warp per signal: A[idx_a][idx_b] += z_a z_b ; B[:, idx_a] += x z_a
-__global__ void __launch_bounds__(256)
-odl_accumulate_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss,
-                      const int32_t* __restrict__ idx, const float* __restrict__ val,
-                      int n, int K, int64_t b, int k, float* __restrict__ A, float* __restrict__ B)
-{
-    const int lane = threadIdx.x & 31;
-    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t i = w; i < b; i += nw) {
-        const int32_t* ii = idx + i * k;
-        const float* vv = val + i * k;
-        // A: k*k pairs spread over the lanes
-        for (int p = lane; p < k * k; p += 32) {
-            int a = p / k, c = p % k;
-            int ia = ii[a], ic = ii[c];
-            if (ia >= 0 && ic >= 0) atomicAdd(&A[(int64_t)ia * K + ic], vv[a] * vv[c]);
-        }
-        // B: n features over the lanes, k atoms
-        for (int f = lane; f < n; f += 32) {
-            const float x = X[(int64_t)f * xfs + i * xss];
-            for (int a = 0; a < k; ++a) {
-                int ia = ii[a];
-                if (ia >= 0) atomicAdd(&B[(int64_t)f * K + ia], x * vv[a]);
-            }
-        }
+    extern __shared__ int32_t sh[];            // counts / cursors [K]
+    __shared__ int32_t wtot[32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int c = t; c < K; c += 1024) sh[c] = 0;
+    __syncthreads();
+    for (int64_t e = t; e < E; e += 1024) {
+        const int a = idx[e];
+        if (a >= 0 && val[e] != 0.f) atomicAdd(&sh[a], 1);
+    }
+    __syncthreads();
+    // exclusive scan: every thread owns 4 consecutive atoms (K <= 4096)
+    int32_t v[4], sum = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const int c = t * 4 + q; v[q] = (c < K) ? sh[c] : 0; sum += v[q]; }
+    int32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const int32_t w = wtot[lane];
+        int32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int32_t u = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += u; }
+        wtot[lane] = winc - w;
+    }
+    __syncthreads();
+    int32_t base = wtot[warp] + inc - sum;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int c = t * 4 + q;
+        if (c < K) { rowptr[c] = base; sh[c] = base; }
+        base += v[q];
+        if (c == K - 1) rowptr[K] = base;
+    }
+    __syncthreads();
+    for (int64_t e = t; e < E; e += 1024) {
+        const int a = idx[e];
+        if (a >= 0 && val[e] != 0.f) entries[atomicAdd(&sh[a], 1)] = (int32_t)e;
     }
 }
 
-// one warp per atom: u = D[:,c] + (B[:,c] - DA[:,c]) / (A[c,c] + eps); clamp; normalise
+// A = beta A + Z Z^T, B = beta B + X Z^T, one CTA per atom a:   row a of A and column a of B            (:84-85)
+//   A[a][c] = beta A[a][c] + sum over the users i of a of z_ia z_ic
+//   B[f][a] = beta B[f][a] + sum over the users i of a of x_if z_ia
+// Fixed summation order, hence bitwise reproducible and identical on every rank that sees the same minibatch: the
+// atom's list is sorted (bitonic, in shared memory), cut into ODL_WARPS contiguous slices, every warp walks its slice
+// in ascending order into its own partial row (lanes = the k codes of a signal / the features), and the partial rows
+// are added in warp order.  An atom that most signals of the minibatch use (the "mean" atom of non-negative
+// descriptors has ~b users) is thus neither a sequential tail nor a source of run-to-run differences.
+// beta == 0 writes the sums alone (0 * x of the reference without its NaN propagation: beta_0 = 0 exists to wipe the
+// statistics).
+constexpr int ODL_WARPS = 8;
+constexpr int ODL_THREADS = ODL_WARPS * 32;
+__global__ void __launch_bounds__(ODL_THREADS)
+odl_accumulate_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss,
+                      const int32_t* __restrict__ idx, const float* __restrict__ val,
+                      const int32_t* __restrict__ rowptr, const int32_t* __restrict__ entries,
+                      int n, int K, int k, int list_cap /* power of two >= longest list */, float beta,
+                      float* __restrict__ A, float* __restrict__ B)
+{
+    extern __shared__ float smf[];
+    const int ldp = K + n;                                  // a warp's partial: [K] new terms of row a of A, [n] of column a of B
+    float* part = smf;                                      // [ODL_WARPS][ldp]
+    int32_t* slist = reinterpret_cast<int32_t*>(smf + (size_t)ODL_WARPS * ldp);      // [list_cap]
+    const int a = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int lo = rowptr[a], cnt = rowptr[a + 1] - lo;
+    if (cnt == 0) {                                         // nobody uses the atom in this minibatch: only the decay
+        float* Arow = A + (int64_t)a * K;
+        for (int c = t; c < K; c += ODL_THREADS) Arow[c] = (beta == 0.f) ? 0.f : beta * Arow[c];
+        for (int f = t; f < n; f += ODL_THREADS) B[(int64_t)f * K + a] = (beta == 0.f) ? 0.f : beta * B[(int64_t)f * K + a];
+        return;
+    }
+    int P = 1;
+    while (P < cnt) P <<= 1;                                // P <= list_cap
+    for (int p = t; p < P; p += ODL_THREADS) slist[p] = (p < cnt) ? entries[lo + p] : 0x7fffffff;
+    const int active = min(ODL_WARPS, (cnt + 3) / 4);        // warps that get users (at least 4 users per warp)
+    for (int c = t; c < active * ldp; c += ODL_THREADS) part[c] = 0.f;
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1) {             // bitonic sort, ascending
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int p = t; p < P / 2; p += ODL_THREADS) {
+                const int i0 = 2 * p - (p & (stride - 1));
+                const int i1 = i0 + stride;
+                const bool up = (i0 & size) == 0;
+                const int32_t x = slist[i0], y = slist[i1];
+                if ((x > y) == up) { slist[i0] = y; slist[i1] = x; }
+            }
+            __syncthreads();
+        }
+    }
+    if (warp < active) {
+        const int per = (cnt + active - 1) / active;
+        const int p0 = warp * per, p1 = min(cnt, p0 + per);
+        float* dA = part + (size_t)warp * ldp;
+        float* dB = dA + K;
+        for (int p = p0; p < p1; ++p) {                     // this warp's users in ascending order
+            const int32_t e = slist[p];
+            const int64_t i = e / k;
+            const float za = val[e];
+            for (int j = lane; j < k; j += 32) {
+                const int c = idx[i * k + j];
+                if (c >= 0) dA[c] = fmaf(za, val[i * k + j], dA[c]);           // distinct atoms inside one code: no conflict
+            }
+            for (int f = lane; f < n; f += 32) dB[f] = fmaf(X[(int64_t)f * xfs + i * xss], za, dB[f]);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    float* Arow = A + (int64_t)a * K;
+    for (int c = t; c < ldp; c += ODL_THREADS) {
+        float s = 0.f;
+        for (int w = 0; w < active; ++w) s += part[(size_t)w * ldp + c];        // fixed order
+        if (c < K) Arow[c] = (beta == 0.f) ? s : fmaf(beta, Arow[c], s);
+        else { float* bp = B + (int64_t)(c - K) * K + a; *bp = (beta == 0.f) ? s : fmaf(beta, *bp, s); }
+    }
+}
+
+// one warp per atom: u = D[:,c] + (B[:,c] - DA[:,c]) / (A[c,c] + eps); clamp; normalise.  DA arrives as `splits` partial
+// products over slices of the contraction (tensor-core GEMM, odl_gemm_tc.cu; splits == 1 for the SIMT GEMM): they are
+// added here in split order — fixed, hence deterministic.
 __global__ void __launch_bounds__(256)
 odl_update_kernel(float* __restrict__ D, int64_t ldd, const float* __restrict__ A,
-                  const float* __restrict__ B, const float* __restrict__ DA, int n, int K, int non_neg)
+                  const float* __restrict__ B, const float* __restrict__ DA, int splits, int n, int K, int non_neg)
 {
     const int lane = threadIdx.x & 31;
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -64,7 +160,9 @@ odl_update_kernel(float* __restrict__ D, int64_t ldd, const float* __restrict__ 
         int f = lane + 32 * q;
         float v = 0.f;
         if (f < n) {
-            v = inv * (B[(int64_t)f * K + c] - DA[(int64_t)f * K + c]) + D[(int64_t)f * ldd + c];
+            float da = 0.f;
+            for (int s = 0; s < splits; ++s) da += DA[((int64_t)s * n + f) * K + c];
+            v = inv * (B[(int64_t)f * K + c] - da) + D[(int64_t)f * ldd + c];
             if (non_neg && v < 0.f) v = 0.f;                                  // :96-97
         }
         u[q] = v;
@@ -84,31 +182,45 @@ odl_update_kernel(float* __restrict__ D, int64_t ldd, const float* __restrict__ 
 
 using namespace lys;
 
+extern "C" size_t lys_odl_accumulate_workspace_bytes(int K, int64_t b, int k)
+{
+    if (K < 1 || b < 0 || k < 1) return 0;
+    return align_up((size_t)(K + 1) * 4, 256) + align_up((size_t)std::max<int64_t>(b * k, 1) * 4, 256) + 256;
+}
+
 extern "C" int lys_odl_accumulate(const float* Xb, int64_t xfs, int64_t xss, const int32_t* idx, const float* val,
-                                  int n, int K, int64_t b, int k, float beta, float* A, float* B, void* stream_)
+                                  int n, int K, int64_t b, int k, float beta, float* A, float* B,
+                                  void* workspace, size_t workspace_bytes, void* stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     LYS_CHECK_ARG(A && B, "lys_odl_accumulate: null statistics");
     LYS_CHECK_ARG(n >= 1 && n <= LYS_MAX_FEATURES && K >= 1 && K <= LYS_MAX_ATOMS && b >= 0 && k >= 1 && k <= LYS_MAX_NONZERO,
                   "lys_odl_accumulate: bad shape");
-    const int blocks = sm_count() * 4;
-    if (beta == 0.f) {       // beta_0 = 0 wipes the statistics exactly (0 * x), also for inf/nan-free inputs
-        LYS_CUDA(cudaMemsetAsync(A, 0, sizeof(float) * (size_t)K * K, stream));
-        LYS_CUDA(cudaMemsetAsync(B, 0, sizeof(float) * (size_t)n * K, stream));
-    } else if (beta != 1.f) {
-        scale_kernel<<<blocks, 256, 0, stream>>>(A, (int64_t)K * K, beta);
-        scale_kernel<<<blocks, 256, 0, stream>>>(B, (int64_t)n * K, beta);
-        LYS_LAUNCH_CHECK("scale_kernel");
+    LYS_CHECK_ARG(b * (int64_t)k < (1ll << 31), "lys_odl_accumulate: b*k must fit int32");
+    LYS_CHECK_ARG(b == 0 || (Xb && idx && val), "lys_odl_accumulate: null pointer");
+    if (!workspace || workspace_bytes < lys_odl_accumulate_workspace_bytes(K, b, k)) {
+        set_error("lys_odl_accumulate: workspace too small");
+        return LYS_EWORKSPACE;
     }
-    if (b == 0) return LYS_OK;
-    LYS_CHECK_ARG(Xb && idx && val, "lys_odl_accumulate: null pointer");
-    int64_t want = (b + 7) / 8;
-    odl_accumulate_kernel<<<(unsigned)std::min<int64_t>(want, blocks * 4), 256, 0, stream>>>(Xb, xfs, xss, idx, val, n, K, b, k, A, B);
+    int32_t* rowptr = reinterpret_cast<int32_t*>(workspace);
+    int32_t* entries = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(workspace) + align_up((size_t)(K + 1) * 4, 256));
+    odl_csr_kernel<<<1, 1024, sizeof(int32_t) * (size_t)K, stream>>>(idx, val, b * (int64_t)k, K, rowptr, entries);
+    LYS_LAUNCH_CHECK("odl_csr_kernel");
+    int list_cap = 1;                                         // an atom has at most b users (one entry per signal)
+    while (list_cap < b) list_cap <<= 1;
+    const size_t smem = sizeof(float) * (size_t)ODL_WARPS * (K + n) + sizeof(int32_t) * (size_t)list_cap;
+    if (smem > 200 * 1024) { set_error("lys_odl_accumulate: minibatch of %lld signals with K=%d does not fit the statistics kernel's shared memory", (long long)b, K); return LYS_EUNSUPPORTED; }
+    LYS_CUDA(cudaFuncSetAttribute(odl_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    odl_accumulate_kernel<<<K, ODL_THREADS, smem, stream>>>(Xb, xfs, xss, idx, val, rowptr, entries, n, K, k, list_cap, beta, A, B);
     LYS_LAUNCH_CHECK("odl_accumulate_kernel");
     return LYS_OK;
 }
 
-extern "C" size_t lys_odl_update_workspace_bytes(int n, int K) { return align_up((size_t)n * K * 4, 256); }
+extern "C" size_t lys_odl_update_workspace_bytes(int n, int K)
+{
+    if (n < 1 || K < 1) return 0;
+    return align_up((size_t)n * K * 4 * (size_t)std::max(1, da_gemm_tc_splits(K)), 256);
+}
 
 extern "C" int lys_odl_update_dict(float* D, int64_t ldd, const float* A, const float* B, int n, int K,
                                    int non_neg, void* workspace, size_t workspace_bytes, void* stream_)
@@ -118,9 +230,16 @@ extern "C" int lys_odl_update_dict(float* D, int64_t ldd, const float* A, const 
     LYS_CHECK_ARG(n >= 1 && n <= LYS_MAX_FEATURES && K >= 1 && K <= LYS_MAX_ATOMS && ldd >= K, "lys_odl_update_dict: bad shape");
     if (workspace_bytes < lys_odl_update_workspace_bytes(n, K)) { set_error("lys_odl_update_dict: workspace too small"); return LYS_EWORKSPACE; }
     float* DA = reinterpret_cast<float*>(workspace);
-    int rc = sgemm_strided(D, ldd, 1, A, K, 1, DA, K, 1, n, K, K, stream);      // DA = D A   (:91)
+    int splits = 1;
+    int rc;
+    if (da_gemm_tc_supported(n, K)) {                                          // DA = D A on tcgen05 (:91), partial products
+        splits = da_gemm_tc_splits(K);
+        rc = da_gemm_tc(D, ldd, A, n, K, DA, stream);
+    } else {
+        rc = sgemm_strided(D, ldd, 1, A, K, 1, DA, K, 1, n, K, K, stream);      // n > 128: fp32 SIMT
+    }
     if (rc) return rc;
-    odl_update_kernel<<<(K * 32 + 255) / 256, 256, 0, stream>>>(D, ldd, A, B, DA, n, K, non_neg);
+    odl_update_kernel<<<(K * 32 + 255) / 256, 256, 0, stream>>>(D, ldd, A, B, DA, splits, n, K, non_neg);
     LYS_LAUNCH_CHECK("odl_update_kernel");
     return LYS_OK;
 }

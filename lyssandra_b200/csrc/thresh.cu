@@ -419,6 +419,16 @@ extern "C" int lys_thresh_encode(const float* X, int64_t xfs, int64_t xss, const
                          workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+extern "C" int lys_topk_select(const float* alpha, int K, int64_t N, int k, int32_t* idx, float* val, int32_t* nsel,
+                               float* Z, int64_t zas, int64_t zss, void* stream)
+{
+    LYS_CHECK_ARG(K >= 1 && K <= LYS_MAX_ATOMS && k >= 1 && k <= K && N >= 0, "lys_topk_select: bad shape");
+    if (N == 0) return LYS_OK;
+    LYS_CHECK_ARG(alpha && idx && val, "lys_topk_select: null pointer");
+    LYS_CHECK_ARG(!Z || (zas >= 1 && zss >= 1), "lys_topk_select: bad Z strides");
+    return launch_select(false, alpha, 1.f, nullptr, nullptr, 0, K, N, k, idx, val, nsel, Z, zas, zss, (cudaStream_t)stream);
+}
+
 extern "C" size_t lys_iht_workspace_bytes(int n, int K, int64_t N)
 {
     if (n < 1 || K < 1 || N < 0) return 0;

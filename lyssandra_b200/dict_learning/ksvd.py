@@ -6,7 +6,8 @@ Per outer iteration (ksvd.py:169-229): Batch-OMP encode -> residual from sparse 
 users-of-atom CSR -> one persistent sweep kernel over all atoms (in-place D and coefficient
 refresh) -> host-RNG replacement of unused atoms -> ||X - D Z||^2 -> the reference's patience
 rule, reproduced as written (quirk Q3: it stops after 11 iterations whatever max_iter says).
-Exact K-SVD (approx=False), non_neg and eta (force_mi) are outside the hot path and raise.
+``approx=False`` runs the exact atom update (``ksvd``, :19-43: rank-1 SVD of R_k per atom) on the device as well
+(n <= 64, single GPU); non_neg and eta (force_mi) are outside the hot path and raise.
 """
 from __future__ import annotations
 
@@ -28,6 +29,31 @@ def approx_ksvd(Y, D, X, n_cycles=1, verbose=True, comm=None):
     the reference's dense Z; its ``val`` is refreshed in place, the support never changes)."""
     D, X, unused_atoms, _ = _approx_ksvd_keep_residual(Y, D, X, n_cycles, comm)
     return D, X, unused_atoms
+
+
+def ksvd(Y, D, X, n_cycles=1, verbose=True):
+    """ksvd(Y, D, X) -> (D, X, unused_atoms), D and X mutated in place (ksvd.py:19-43): the exact K-SVD atom update,
+    (d_k, x_k) <- top singular triplet of R_k (the reference: scikit-learn randomized_svd with 10 power iterations;
+    here: eigenvector of R_k R_k^T, csrc/ksvd_exact.cu).  The common sign of (d_k, x_k) is arbitrary in the
+    reference; here it is the one with d_k . d_k_old >= 0.
+
+    Y: (n, N) CUDA tensor, n <= 64; D: (n, K) CUDA tensor; X: engine.SparseCodes."""
+    D, X, unused_atoms, _ = _ksvd_keep_residual(Y, D, X, n_cycles, exact=True)
+    return D, X, unused_atoms
+
+
+def _ksvd_keep_residual(Y, D, X, n_cycles=1, comm=None, exact=False):
+    if not exact:
+        return _approx_ksvd_keep_residual(Y, D, X, n_cycles, comm)
+    if comm is not None:
+        raise NotImplementedError("exact K-SVD (approx=False) runs on one GPU; shard with approx=True")
+    if not isinstance(X, engine.SparseCodes):
+        raise TypeError("ksvd takes engine.SparseCodes (use sparse_encoder.encode_sparse)")
+    R, _ = engine.residual(Y, D, X, want_residual=True, want_error=False)         # :29
+    rowptr, entries = engine.build_atom_csr(X)                                      # :31
+    flags = engine.ksvd_exact_sweep(R, D, X, rowptr, entries, n_cycles=n_cycles)    # :30-41
+    unused_atoms = torch.nonzero(flags).flatten().cpu().tolist()
+    return D, X, unused_atoms, R
 
 
 def _approx_ksvd_keep_residual(Y, D, X, n_cycles=1, comm=None):
@@ -58,8 +84,6 @@ def ksvd_dict_learn(X, n_atoms, init_dict="data", sparse_coder=None, max_iter=20
         # the reference's ksvd_coder default (max_iter=None, ksvd.py:240) only "works" on Python 2, where
         # `0 < None` is False and the loop is silently skipped; say what is wrong instead
         raise ValueError("max_iter must be a non-negative integer (ksvd_coder's default None never ran an iteration in the reference)")
-    if not approx:
-        raise NotImplementedError("exact K-SVD (approx=False) is outside this engine's scope; pass approx=True")
     if non_neg:
         raise NotImplementedError("nn_ksvd (non_neg=True) is outside this engine's scope")
     if eta is not None:
@@ -99,7 +123,7 @@ def ksvd_dict_learn(X, n_atoms, init_dict="data", sparse_coder=None, max_iter=20
         if verbose:
             torch.cuda.synchronize(dev)
         t1 = time.perf_counter()
-        D, _, unused_atoms, R = _approx_ksvd_keep_residual(Xd, D, codes, n_cycles=n_cycles, comm=comm)   # :186
+        D, _, unused_atoms, R = _ksvd_keep_residual(Xd, D, codes, n_cycles=n_cycles, comm=comm, exact=not approx)   # :182-190
         for slot in unused_atoms:                                                               # :199-207
             if len(unused_data) == 0 or (multi and dist.rank != 0):
                 break

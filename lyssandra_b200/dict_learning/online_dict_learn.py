@@ -6,8 +6,8 @@ Per minibatch (:79-98): Batch-OMP encode -> sparse sufficient statistics
 A = beta*A + Z Z^T, B = beta*B + X Z^T -> one GEMM D A with a fused Jacobi column update,
 optional clamp and column normalisation.  Mirrored quirks: beta=None is
 linspace(0,1,n_iter) restarted every epoch, so the first minibatch of every epoch wipes A, B;
-D_init is used without copying and updated in place; the end-of-epoch patience rule is
-reproduced as written."""
+a CUDA-tensor D_init is used without copying and updated in place as in the reference (a NumPy D_init is uploaded, so
+the caller's array is NOT mutated — take the returned D); the end-of-epoch patience rule is reproduced as written."""
 from __future__ import annotations
 
 from itertools import cycle
@@ -20,13 +20,34 @@ from ..utils import gen_batches
 from .utils import init_dictionary
 
 
+def _gather_minibatch(dist, Xb, codes):
+    """all-gather this rank's slice of the minibatch — signals and sparse codes, (n + 2k) words per signal instead of
+    the K x K + n x K statistics an all-reduce would move — so that every rank accumulates the WHOLE minibatch in the
+    same fixed order and ends with bit-identical A, B and D."""
+    import torch.distributed as td
+    b_loc, k = codes.idx.shape
+    n = Xb.shape[0]
+    w = dist.world
+    Xs = Xb.t().contiguous()                                                        # (b_loc, n) signal-major
+    Xall = torch.empty((w * b_loc, n), dtype=torch.float32, device=Xs.device)
+    iall = torch.empty((w * b_loc, k), dtype=torch.int32, device=Xs.device)
+    vall = torch.empty((w * b_loc, k), dtype=torch.float32, device=Xs.device)
+    td.all_gather_into_tensor(Xall, Xs, group=dist.group)
+    td.all_gather_into_tensor(iall, codes.idx.contiguous(), group=dist.group)
+    td.all_gather_into_tensor(vall, codes.val.contiguous(), group=dist.group)
+    return Xall.t(), engine.SparseCodes(iall, vall, (iall >= 0).sum(dim=1).to(torch.int32), codes.n_atoms)
+
+
 def online_dict_learn(X, n_atoms, sparse_coder=None, batch_size=None, A=None, B=None, D_init=None,
                       beta=None, n_epochs=1, verbose=False, n_jobs=1, non_neg=False, mmap=False,
-                      allreduce=None):
+                      dist=None):
     """-> (D, A, B).  CUDA tensors in -> CUDA tensors out; NumPy in -> NumPy out.
-    ``allreduce`` (callable taking a tensor, summing it in place over ranks) makes the
-    sufficient statistics global when the minibatch columns are sharded over GPUs; it is
-    exact because the block update is Jacobi (:91-94)."""
+
+    Multi-GPU (one process per GPU): pass ``dist`` (distributed.DistContext).  X is then THIS rank's slice of every
+    minibatch (``batch_size`` = signals per rank and minibatch, the same on every rank): the slices are encoded
+    independently, all-gathered as (signal, idx, val), and the statistics and the dictionary update run replicated and
+    order-deterministic on every rank — exact, because the block update is Jacobi (:91-94), and bit-identical to the
+    single-GPU run on the gathered minibatch."""
     sparse_coder.verbose = False                                                   # :41
     numpy_in = not (torch.is_tensor(X) and X.is_cuda)
     Xd = engine.as_device_matrix(X, None if numpy_in else X.device)
@@ -49,6 +70,7 @@ def online_dict_learn(X, n_atoms, sparse_coder=None, batch_size=None, A=None, B=
     else:
         beta_seq = np.zeros(n_iter) + beta
 
+    multi = dist is not None and dist.world > 1
     max_patience = 10
     error_curr = 0
     error_prev = 0
@@ -57,14 +79,9 @@ def online_dict_learn(X, n_atoms, sparse_coder=None, batch_size=None, A=None, B=
         for i, batch in zip(range(n_iter), cycle(batch_idx)):                      # :79
             Xb = Xd[:, batch.start:batch.stop]
             codes = sparse_coder.encode_sparse(Xb, D)                              # :82
-            if allreduce is None:
-                engine.odl_accumulate_(Xb, codes, beta_seq[i], A, B)               # :84-85
-            else:
-                A.mul_(float(beta_seq[i])); B.mul_(float(beta_seq[i]))
-                dA = torch.zeros_like(A); dB = torch.zeros_like(B)
-                engine.odl_accumulate_(Xb, codes, 1.0, dA, dB)
-                allreduce(dA); allreduce(dB)
-                A.add_(dA); B.add_(dB)
+            if multi:
+                Xb, codes = _gather_minibatch(dist, Xb, codes)
+            engine.odl_accumulate_(Xb, codes, beta_seq[i], A, B)                   # :84-85
             engine.odl_update_dict_(D, A, B, non_neg=non_neg)                      # :91-98
         if e < n_epochs - 1:                                                       # :101-118
             if patience >= max_patience:
@@ -74,8 +91,8 @@ def online_dict_learn(X, n_atoms, sparse_coder=None, batch_size=None, A=None, B=
                 Xb = Xd[:, batch.start:batch.stop]
                 codes = sparse_coder.encode_sparse(Xb, D)
                 _, err = engine.residual(Xb, D, codes, want_residual=False, want_error=True)
-                if allreduce is not None:
-                    allreduce(err)
+                if multi:
+                    dist.allreduce_sum_(err)
                 error_curr += float(err.item())
             if verbose:
                 print("end of epoch %d: error %.6g (difference %.6g)" % (e, error_curr, error_curr - error_prev))

@@ -100,7 +100,8 @@ def gram(D):
     n, K = D.shape
     G = torch.empty((K, K), dtype=torch.float32, device=D.device)
     with torch.cuda.device(D.device):
-        nat.check(lib.lys_gram(_ptr(D), D.stride(0), n, K, _ptr(G), _stream_ptr(D.device)))
+        ws = workspace(D.device, lib.lys_gram_workspace_bytes(n, K), tag="gram")
+        nat.check(lib.lys_gram_ws(_ptr(D), D.stride(0), n, K, _ptr(G), _ptr(ws), ws.numel(), _stream_ptr(D.device)))
     return G
 
 
@@ -130,6 +131,63 @@ def bomp_encode(X, D, k, G=None, dense=False, screen=False):
             _ptr(X), X.stride(0), X.stride(1), _ptr(D), D.stride(0), _ptr(G), n, K, N, k,
             _ptr(idx), _ptr(val), _ptr(nsel), _ptr(Zt), 1, K, _ptr(ws), ws.numel(),
             nat.BOMP_SCREEN if screen else 0, _stream_ptr(dev)))
+    codes = SparseCodes(idx, val, nsel, K)
+    if dense:
+        return codes, Zt.t()
+    return codes
+
+
+def omp_encode(X, D, k=None, tol=None, G=None, dense=False):
+    """The reference's plain `omp` coder (lyssa/sparse_coding.py:618-625 -> :19-66) on device tensors.
+    ``k`` = n_nonzero_coefs (then the reference forces tol = 1e-10 and stops at k atoms) or, with ``k`` None,
+    ``tol`` alone (continue while ||r|| >= tol; at most nat.OMP_MAX_NONZERO atoms per signal are supported and a signal
+    that needs more raises).  Returns like bomp_encode."""
+    lib = nat.load()
+    n, N = X.shape
+    n2, K = D.shape
+    if n != n2:
+        raise ValueError("X has %d features but D has %d" % (n, n2))
+    if k is None and tol is None:
+        raise ValueError("algorithm 'omp' needs params['n_nonzero_coefs'] or params['tol']")
+    strict = k is not None                                             # sparse_coding.py:27-34
+    kmax = int(k) if strict else min(K, n, nat.OMP_MAX_NONZERO)
+    tol = 1e-10 if strict else float(tol)
+    dev = X.device
+    with torch.cuda.device(dev):
+        if G is None:
+            G = gram(D)
+        idx = torch.empty((N, kmax), dtype=torch.int32, device=dev)
+        val = torch.empty((N, kmax), dtype=torch.float32, device=dev)
+        nsel = torch.empty((N,), dtype=torch.int32, device=dev)
+        Zt = torch.empty((N, K), dtype=torch.float32, device=dev) if dense else None
+        trunc = torch.zeros((1,), dtype=torch.int32, device=dev)
+        ws = workspace(dev, lib.lys_omp_workspace_bytes(n, K, N, kmax))
+        nat.check(lib.lys_omp_encode(
+            _ptr(X), X.stride(0), X.stride(1), _ptr(D), D.stride(0), _ptr(G), n, K, N, kmax, tol, 1 if strict else 0,
+            _ptr(idx), _ptr(val), _ptr(nsel), _ptr(Zt), 1, K, _ptr(trunc), _ptr(ws), ws.numel(), _stream_ptr(dev)))
+        if not strict and int(trunc.item()) > 0:
+            raise NotImplementedError("'omp' with tol=%g: %d signal(s) need more than %d atoms (the engine's limit per signal)"
+                                      % (tol, int(trunc.item()), kmax))
+    codes = SparseCodes(idx, val, nsel, K)
+    if dense:
+        return codes, Zt.t()
+    return codes
+
+
+def topk_select(Alpha, k, dense=True):
+    """thresholding / soft_thresholding on a given correlation matrix Alpha (K, N) (lyssa/sparse_coding.py:416-425,
+    lyssa/feature_encoding.py:26-37): the k largest SIGNED entries of every column."""
+    lib = nat.load()
+    K, N = Alpha.shape
+    At = Alpha.t().contiguous()                                        # (N, K) signal-major, what the selection kernels read
+    dev = Alpha.device
+    k = int(k)
+    with torch.cuda.device(dev):
+        idx = torch.empty((N, k), dtype=torch.int32, device=dev)
+        val = torch.empty((N, k), dtype=torch.float32, device=dev)
+        nsel = torch.empty((N,), dtype=torch.int32, device=dev)
+        Zt = torch.empty((N, K), dtype=torch.float32, device=dev) if dense else None
+        nat.check(lib.lys_topk_select(_ptr(At), K, N, k, _ptr(idx), _ptr(val), _ptr(nsel), _ptr(Zt), 1, K, _stream_ptr(dev)))
     codes = SparseCodes(idx, val, nsel, K)
     if dense:
         return codes, Zt.t()
@@ -287,6 +345,23 @@ def approx_ksvd_sweep(R, D, codes: SparseCodes, rowptr, entries, n_cycles=1, com
     return unused
 
 
+def ksvd_exact_sweep(R, D, codes: SparseCodes, rowptr, entries, n_cycles=1):
+    """In-place EXACT K-SVD sweep over all atoms (ksvd.py:19-43): (d, x) <- top singular triplet of R_k.  Mutates D,
+    codes.val and R; returns the int32 (K,) unused-atom flags.  n <= 64, single GPU."""
+    lib = nat.load()
+    n, K = D.shape
+    N, k = codes.idx.shape
+    dev = D.device
+    if D.stride(1) != 1:
+        raise ValueError("D must have contiguous rows")
+    unused = torch.empty((K,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        ws = workspace(dev, lib.lys_ksvd_exact_workspace_bytes(n, K), tag="sweep")
+        nat.check(lib.lys_ksvd_exact_sweep(_ptr(R), _ptr(D), D.stride(0), _ptr(codes.val), _ptr(rowptr), _ptr(entries),
+                                           n, K, N, k, int(n_cycles), _ptr(unused), _ptr(ws), ws.numel(), _stream_ptr(dev)))
+    return unused
+
+
 def norm_cols_(D):
     """In-place D[:,c] /= (||D[:,c]|| + eps)  (lyssa/utils/math.py:65-71)."""
     lib = nat.load()
@@ -312,14 +387,16 @@ def gather_cols_(X, cols, D, dst_cols=None):
 
 
 def odl_accumulate_(Xb, codes: SparseCodes, beta, A, B):
-    """A = beta*A + Z Z^T ; B = beta*B + X Z^T  (online_dict_learn.py:84-85), in place."""
+    """A = beta*A + Z Z^T ; B = beta*B + X Z^T  (online_dict_learn.py:84-85), in place, fixed summation order."""
     lib = nat.load()
     n, b = Xb.shape
     K = A.shape[0]
     dev = A.device
     with torch.cuda.device(dev):
+        ws = workspace(dev, lib.lys_odl_accumulate_workspace_bytes(K, b, codes.k), tag="odl_acc")
         nat.check(lib.lys_odl_accumulate(_ptr(Xb), Xb.stride(0), Xb.stride(1), _ptr(codes.idx), _ptr(codes.val),
-                                         n, K, b, codes.k, float(beta), _ptr(A), _ptr(B), _stream_ptr(dev)))
+                                         n, K, b, codes.k, float(beta), _ptr(A), _ptr(B), _ptr(ws), ws.numel(),
+                                         _stream_ptr(dev)))
 
 
 def odl_update_dict_(D, A, B, non_neg=False):

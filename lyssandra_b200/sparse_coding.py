@@ -3,8 +3,8 @@
 :629-635 the 'bomp' branch, :706 the unknown-algorithm error, :708-726 dispatch) and the two
 thresholding coders that share its correlation front end (:636-641 'thresh', :671-690 'iht').
 
-``algorithm`` 'bomp', 'thresh' and 'iht' run — on the GPU, through liblyssa_b200.so.  The
-reference's other coders are outside this engine's scope and raise
+``algorithm`` 'bomp', 'omp' (:618-625 -> :19-66, the reference's default), 'thresh' and 'iht' run — on the GPU,
+through liblyssa_b200.so.  The reference's other coders are outside this engine's scope and raise
 NotImplementedError rather than silently running on the CPU; an unknown name raises ValueError
 exactly like the reference.  The public attributes (algorithm, params, n_jobs, verbose, mmap, name) are plain
 and mutable because reference callers mutate them (ksvd.py:159, online_dict_learn.py:41).
@@ -68,7 +68,9 @@ class sparse_encoder(object):
         return self._encode_host(Xh, Dh, k, dense=True)[3]
 
     def _encode_device(self, Xd, Dd, k, dense, G=None):
-        if self.algorithm == "thresh":
+        if self.algorithm == "omp":
+            out = engine.omp_encode(Xd, Dd, k, tol=self.params.get("tol"), G=G, dense=dense)
+        elif self.algorithm == "thresh":
             out = engine.thresh_encode(Xd, Dd, k, dense=dense)
         elif self.algorithm == "iht":
             out = engine.iht_encode(Xd, Dd, k, self.params.get("eta"), self.params.get("n_iter"), dense=dense)
@@ -97,13 +99,17 @@ class sparse_encoder(object):
     # --------------------------------------------------------------------------- helpers
     def _check(self, n_atoms=None):
         alg = self.algorithm
-        if alg not in ("bomp", "thresh", "iht"):
+        if alg not in ("bomp", "omp", "thresh", "iht"):
             if alg in _REFERENCE_ALGORITHMS:
                 raise NotImplementedError(
-                    "algorithm %r is outside the B200 engine's scope: 'bomp', 'thresh' and 'iht' are "
+                    "algorithm %r is outside the B200 engine's scope: 'bomp', 'omp', 'thresh' and 'iht' are "
                     "implemented (no CPU fallback by design)" % (alg,))
             raise ValueError("Sparse optimizer not found.")          # sparse_coding.py:706
         k = self.params.get("n_nonzero_coefs")
+        if alg == "omp":                                             # :27-34: n_nonzero_coefs, or tol alone
+            if k is None and self.params.get("tol") is None:
+                raise ValueError("algorithm 'omp' needs params['n_nonzero_coefs'] or params['tol']")
+            return None if k is None else int(k)
         pct = self.params.get("nonzero_percentage")
         if alg != "bomp" and pct is not None:
             if n_atoms is None:

@@ -70,6 +70,23 @@ def ksvd_exact_section(ref):
                         unused=np.array(unused, dtype=np.int32), seed=5)
 
 
+def gen_omp(ref):
+    """'omp' (the reference's default algorithm, sparse_coding.py:618-625 -> :19-66) and feature_encoder's
+    soft_thresholding (feature_encoding.py:26-37, loaded from the reference file) through the LIVE reference."""
+    X = lo.synthetic_patches(300, 64, seed=60)
+    D = lo.synthetic_dictionary(256, 64, seed=61)
+    Xd, Dd = X.astype(float), D.astype(float)
+    out = {"X": np.ascontiguousarray(X), "D": D}
+    for tag, params in (("k5", {"n_nonzero_coefs": 5}), ("tol1p2", {"tol": 1.2}), ("tol0p8", {"tol": 0.8})):
+        Z = ref.sparse_encoder(algorithm="omp", params=params, verbose=False).encode(Xd, Dd)
+        out["Z_" + tag] = Z.astype(np.float32)
+    Ds = (D * np.linspace(0.5, 2.0, 256, dtype=np.float32)[None, :]).astype(np.float32)      # NOT unit norm: omp is still exact least squares
+    out["D_scaled"] = Ds
+    out["Z_scaled_k4"] = ref.sparse_encoder(algorithm="omp", params={"n_nonzero_coefs": 4}, verbose=False).encode(Xd, Ds.astype(float)).astype(np.float32)
+    out["Z_soft_k7"] = ref.soft_thresholding(np.dot(Dd.T, Xd), n_nonzero_coefs=7).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "omp.npz"), **out)
+
+
 def main():
     ref = rl.load()
     os.makedirs(OUT, exist_ok=True)

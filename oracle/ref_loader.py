@@ -221,7 +221,15 @@ def load():
     ds_ns.update(n_angles=8, n_bins=4, n_samples=16, alpha=9.0, angles=np.array(range(8)) * 2.0 * np.pi / 8)
     sp_ns["DsiftExtractor"] = ds_ns["DsiftExtractor"]
 
+    # feature_encoding.py (Coates & Ng encoders): soft_thresholding / feature_encoder on the same correlations
+    fe_ns = dict(base)
+    fe_ns["run_parallel"] = utils_ns["run_parallel"]
+    _load_defs("lyssa/feature_encoding.py", fe_ns)
+
     ref = _Ref()
+    ref.soft_thresholding = fe_ns["soft_thresholding"]
+    ref.feature_encoder = fe_ns["feature_encoder"]
+    ref.feature_encoder.__call__ = _call_with_stub(fe_ns["feature_encoder"].__call__)
     ref.DsiftExtractor = ds_ns["DsiftExtractor"]
     ref.dsift_extractor = sp_ns["dsift_extractor"]
     ref.sc_spm_extractor = sp_ns["sc_spm_extractor"]

@@ -64,10 +64,10 @@ l2, h2_ = ctx.shard(2048)
 # sharded: every rank takes its slice of each minibatch
 Xparts = torch.cat([Xo[:, m * 2048 + l2: m * 2048 + h2_] for m in range(4)], dim=1)
 Db, Ab, Bb = online_dict_learn(Xparts, K4, sparse_coder=enc5, batch_size=h2_ - l2, D_init=Do.clone(), beta=0.9, n_epochs=1,
-                               allreduce=ctx.allreduce_sum_)
+                               dist=ctx)
 dA = float((Aa - Ab).abs().max() / Aa.abs().max()); dDo = float((Da - Db).abs().max())
-report.update({"odl_rel_dA": dA, "odl_max_dD": dDo})
-ok3 = dA < 1e-4 and dDo < 1e-3
+report.update({"odl_rel_dA": dA, "odl_max_dD": dDo, "odl_bitwise_equal_to_1gpu": bool(torch.equal(Da, Db) and torch.equal(Aa, Ab) and torch.equal(Ba, Bb))})
+ok3 = dA < 1e-6 and dDo < 1e-6
 ex.close()
 okall = torch.tensor([int(ok1 and ok2 and ok2b and ok3)], device=dev); ctx.allreduce_sum_(okall)
 if ctx.rank == 0:

@@ -89,3 +89,36 @@ def dense_to_codes(Z, k):
         idx[i, :len(nz)] = nz
         val[i, :len(nz)] = Z[nz, i]
     return idx, val
+
+
+def omp_trace(X, D, n_nonzero_coefs=None, tol=None):
+    """float64 replay of the oracle's `omp` (lyssa/sparse_coding.py:19-66) that also returns, per column, the
+    smallest relative top-1/top-2 gap of |alpha| met at any step and the smallest relative distance of ||r|| from
+    the stopping threshold at any test of the continue criterion (:27-34) — the decisions float32 can flip."""
+    X = np.asarray(X, dtype=np.float64); D = np.asarray(D, dtype=np.float64)
+    K, N = D.shape[1], X.shape[1]
+    G = D.T @ D
+    Z = np.zeros((K, N)); gap = np.full(N, np.inf); margin = np.full(N, np.inf)
+    thr = 1e-10 if n_nonzero_coefs is not None else tol
+    for i in range(N):
+        x = X[:, i]; r = x.copy(); sel = []; z = None
+        while True:
+            rn = np.linalg.norm(r)
+            margin[i] = min(margin[i], abs(rn - thr) / max(np.linalg.norm(x), 1e-300))
+            if n_nonzero_coefs is not None:
+                if not (len(sel) < n_nonzero_coefs and rn > thr):
+                    break
+            elif not rn >= thr:
+                break
+            a = np.abs(D.T @ r)
+            p = int(np.argmax(a))
+            top = a[p]; a[p] = -1.0
+            gap[i] = min(gap[i], (top - a.max()) / top if top > 0 else 0.0)
+            if p in sel:
+                break
+            sel.append(p)
+            z = np.linalg.solve(G[np.ix_(sel, sel)], D[:, sel].T @ x)
+            r = x - D[:, sel] @ z
+        if sel:
+            Z[sel, i] = z
+    return Z, gap, margin

@@ -40,7 +40,7 @@ def test_pure_host_entry_points():
     assert lib.lys_bomp_workspace_bytes(0, 1024, 10, 5) == 0
     assert lib.lys_residual_workspace_bytes(64, 1024, 1000) >= 64 * 1024 * 4
     assert lib.lys_ksvd_sweep_workspace_bytes(64, 1024, 1000, 5) >= 64 * 1024 * 4
-    assert lib.lys_odl_update_workspace_bytes(128, 2048) >= 128 * 2048 * 4
+    assert lib.lys_odl_update_workspace_bytes(128, 2048) >= 128 * 2048 * 4 and lib.lys_odl_accumulate_workspace_bytes(2048, 4096, 5) >= 4096 * 5 * 4
     # argument validation happens before any CUDA call
     rc = lib.lys_bomp_encode(None, 1, 64, None, 1024, None, 64, 1024, 10, 0, None, None, None, None, 1, 1024, None, 0, None)
     assert rc == _native.LYS_EINVAL

@@ -308,3 +308,23 @@ def test_dictionary_scale_does_not_matter_to_the_fused_path():
     b1 = engine.bomp_encode(X, torch.from_numpy(Dh).to(DEV), 1)
     b2 = engine.bomp_encode(X, torch.from_numpy(Dh * np.float32(4096.0)).to(DEV), 1)
     assert int((b1.idx != b2.idx).sum()) <= N // 500
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_n_jobs_spreads_host_arrays_over_gpus_bit_identically():
+    """sparse_encoder(n_jobs=G).encode(numpy): contiguous column blocks over G GPUs, one host thread per GPU (the
+    analogue of run_parallel's process pool, lyssa/utils/__init__.py:92-146).  The per-device pipelines take their own
+    locks, so the devices run concurrently; the result must equal the one-GPU result bit for bit."""
+    import time
+    N, n, K, k = 400000, 64, 1024, 5
+    X = lo.synthetic_patches(N, n, seed=17); D = lo.synthetic_dictionary(K, n, seed=18)
+    one = sparse_encoder("bomp", {"n_nonzero_coefs": k}, n_jobs=1, verbose=False)
+    two = sparse_encoder("bomp", {"n_nonzero_coefs": k}, n_jobs=2, verbose=False)
+    i1, v1, s1 = one.encode_sparse_host(X, D)
+    i2, v2, s2 = two.encode_sparse_host(X, D)
+    assert np.array_equal(i1, i2) and np.array_equal(v1, v2) and np.array_equal(s1, s2)
+    Z1 = one.encode(X[:, :50000], D); Z2 = two.encode(X[:, :50000], D)
+    assert np.array_equal(Z1, Z2)
+    two.encode_sparse_host(X, D)                                # warm both pipelines
+    t0 = time.perf_counter(); one.encode_sparse_host(X, D); t1 = time.perf_counter(); two.encode_sparse_host(X, D); t2 = time.perf_counter()
+    print("n_jobs=1 %.1f ms, n_jobs=2 %.1f ms" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3))

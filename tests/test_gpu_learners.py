@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from oracle import lyssa_oracle as lo  # noqa: E402
 from lyssandra_b200 import engine  # noqa: E402
 from lyssandra_b200.sparse_coding import sparse_encoder  # noqa: E402
-from lyssandra_b200.dict_learning import (approx_ksvd, ksvd_dict_learn, ksvd_coder, online_dict_learn,  # noqa: E402
+from lyssandra_b200.dict_learning import (approx_ksvd, ksvd, ksvd_dict_learn, ksvd_coder, online_dict_learn,  # noqa: E402
                                           online_dictionary_coder, dictionary_learner, init_dictionary, approx_error)
 
 pytestmark = pytest.mark.gpu
@@ -160,6 +160,63 @@ def test_sweep_wide_features():
     assert np.max(np.abs(codes.val.cpu().numpy() - vo)) <= 1e-4 * np.max(np.abs(vo))
 
 
+def _sign_aligned(D, V, Dref):
+    sgn = np.sign(np.sum(D * Dref, axis=0)); sgn[sgn == 0] = 1.0
+    return D * sgn, V * sgn[:, None]
+
+
+def test_exact_ksvd_matches_golden(golden):
+    """one sweep of the exact atom update (ksvd.py:19-43) against the live reference's result
+    (tests/golden/ksvd_exact.npz).  The reference's randomized_svd leaves the common sign of (atom, coefficient row)
+    arbitrary and is itself converged to ~1e-6: compare after sign alignment."""
+    g = golden("ksvd_exact")
+    K = g["D0"].shape[1]
+    Z0 = g["Z0"]
+    k = int((Z0 != 0).sum(axis=0).max())
+    N = Z0.shape[1]
+    idx = -np.ones((N, k), dtype=np.int32); val = np.zeros((N, k), dtype=np.float32)
+    for i in range(N):
+        nz = np.flatnonzero(Z0[:, i])
+        idx[i, :len(nz)] = nz; val[i, :len(nz)] = Z0[nz, i]
+    X = torch.from_numpy(g["X"]).to(DEV); D = torch.from_numpy(g["D0"].astype(np.float32)).to(DEV)
+    codes = _codes(idx, val, K)
+    e0 = approx_error(D, codes, X)
+    D2, codes2, unused = ksvd(X, D, codes, n_cycles=1, verbose=False)
+    assert D2 is D and codes2 is codes and unused == list(g["unused"]) == [9]
+    Zd = _dense(idx, codes.val.cpu().numpy().astype(np.float64), K)
+    Da, Za = _sign_aligned(D.cpu().numpy().astype(np.float64), Zd, g["D1"])
+    assert np.max(np.abs(Da - g["D1"])) <= 1e-4
+    assert np.max(np.abs(Za - g["Z1"])) <= 1e-4 * np.max(np.abs(g["Z1"]))
+    used = [c for c in range(K) if c != 9]
+    assert np.max(np.abs(np.linalg.norm(D.cpu().numpy()[:, used], axis=0) - 1)) < 1e-5
+    assert approx_error(D, codes, X) < e0
+
+
+def test_exact_ksvd_vs_lapack_oracle_and_learner():
+    """seeded, cfg-like density (every CTA holds users of every atom; popular atoms exceed the 256 staged rows): D x^T of
+    every atom against the oracle's LAPACK-SVD sweep; then the outer loop with approx=False decreases the objective"""
+    n, K, N, k = 64, 64, 60000, 4
+    Xh = lo.synthetic_patches(N, n, seed=91); Dh = lo.synthetic_dictionary(K, n, seed=92)
+    X = torch.from_numpy(np.ascontiguousarray(Xh)).to(DEV); D = torch.from_numpy(Dh).to(DEV).clone()
+    codes = _enc(k).encode_sparse(X, D)
+    idx = codes.idx.cpu().numpy(); val0 = codes.val.cpu().numpy().astype(np.float64)
+    Zd = _dense(idx, val0, K)
+    Do, Zo, unused_o = lo.ksvd(Xh.astype(np.float64), Dh.astype(np.float64).copy(), Zd.copy(), n_cycles=1, svd="lapack")
+    _, _, unused = ksvd(X, D, codes)
+    assert unused == list(unused_o)
+    Zg = _dense(idx, codes.val.cpu().numpy().astype(np.float64), K)
+    Da, Za = _sign_aligned(D.cpu().numpy().astype(np.float64), Zg, Do)
+    assert np.max(np.abs(Da - Do)) <= 2e-4
+    assert np.max(np.abs(Za - Zo)) <= 2e-4 * np.max(np.abs(Zo))
+    eo = np.linalg.norm(Xh - Do @ Zo) ** 2
+    assert abs(approx_error(D, codes, X) - eo) <= 1e-4 * eo
+    hist = []
+    ksvd_dict_learn(X[:, :20000], 32, init_dict=torch.from_numpy(lo.synthetic_dictionary(32, n, seed=93)).to(DEV), sparse_coder=_enc(3),
+                    max_iter=4, approx=False, verbose=False, return_codes=True, history=hist)
+    errs = [h["error"] for h in hist]
+    assert len(errs) == 4 and all(b < a for a, b in zip(errs, errs[1:]))
+
+
 def test_ksvd_dict_learn_matches_golden(golden):
     g = golden("ksvd_learn")
     X = torch.from_numpy(g["X"]).to(DEV)
@@ -189,8 +246,12 @@ def test_ksvd_coder_quirk_q3_and_numpy_io():
     assert errs[-1] < errs[0]
     Z = coder.encode(Xh)
     assert isinstance(Z, np.ndarray) and Z.shape == (128, 1500) and np.all((Z != 0).sum(0) <= 3)
-    with pytest.raises(NotImplementedError):
-        ksvd_dict_learn(torch.zeros((64, 10), device=DEV), 8, sparse_coder=_enc(2), approx=False)
+    with pytest.raises(NotImplementedError):                           # nn_ksvd stays outside the hot path
+        ksvd_dict_learn(torch.from_numpy(Xh).to(DEV), 8, sparse_coder=_enc(2), approx=True, non_neg=True)
+    with pytest.raises(ValueError, match="max_iter"):                  # the reference's default max_iter=None never iterated
+        ksvd_coder(n_atoms=8, sparse_coder=_enc(2), verbose=False).fit(Xh)
+    with pytest.raises(Exception, match="n <= 64"):                    # the exact atom update is built for n <= 64
+        ksvd_dict_learn(torch.rand((128, 400), device=DEV), 8, sparse_coder=_enc(2), approx=False, max_iter=1, verbose=False)
 
 
 def test_init_dictionary_matches_golden(golden):

@@ -26,11 +26,18 @@ def test_invalid_encoder_raises_like_the_reference():
 
 
 def test_other_reference_coders_do_not_fall_back_to_cpu():
-    se = sparse_encoder(algorithm="omp", params={"n_nonzero_coefs": 4})
-    with pytest.raises(NotImplementedError):
-        se.encode(np.zeros((4, 3)), np.eye(4))
+    for alg in ("nnomp", "group_omp", "sparse_group_omp", "somp", "lasso", "llc"):
+        with pytest.raises(NotImplementedError):
+            sparse_encoder(algorithm=alg, params={"n_nonzero_coefs": 4}).encode(np.zeros((4, 3)), np.eye(4))
     with pytest.raises(ValueError):
         sparse_encoder(algorithm="bomp", params={}).encode(np.zeros((4, 3)), np.eye(4))
+    with pytest.raises(ValueError, match="n_nonzero_coefs.*tol"):
+        sparse_encoder(algorithm="omp", params={}).encode(np.zeros((4, 3)), np.eye(4))
+    # 'omp' (the reference's default algorithm) is served by the device library: without a GPU it fails loudly
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            sparse_encoder(algorithm="omp", params={"n_nonzero_coefs": 2}).encode(np.zeros((4, 3), dtype=np.float32), np.eye(4, dtype=np.float32))
 
 
 def test_thresholding_coder_parameters():
@@ -105,13 +112,25 @@ def _gloo_worker(rank, world, port, N, out):
     cnt = torch.tensor([hi_ - lo_], dtype=torch.int64)
     ctx.allreduce_sum_(cnt)
     gathered = ctx.allgather_bytes(bytes([rank]) * 4)
+    # the ODL minibatch exchange: every rank ends with the whole minibatch (signals + codes) in rank order
+    from lyssandra_b200 import engine
+    from lyssandra_b200.dict_learning.online_dict_learn import _gather_minibatch
+    b_loc, k, n = 5, 3, 4
+    Xb = torch.arange(n * b_loc, dtype=torch.float32).reshape(n, b_loc) + 100 * rank
+    codes = engine.SparseCodes(torch.full((b_loc, k), rank, dtype=torch.int32), torch.full((b_loc, k), float(rank)),
+                               torch.full((b_loc,), k, dtype=torch.int32), 7)
+    Xall, call = _gather_minibatch(ctx, Xb, codes)
+    want_X = torch.cat([torch.arange(n * b_loc, dtype=torch.float32).reshape(n, b_loc) + 100 * r for r in range(world)], dim=1)
+    ok_mb = (tuple(Xall.shape) == (n, world * b_loc) and torch.equal(Xall, want_X) and call.n_atoms == 7
+             and torch.equal(call.idx[:, 0], torch.arange(world, dtype=torch.int32).repeat_interleave(b_loc))
+             and torch.equal(call.val[:, 0], torch.arange(world, dtype=torch.float32).repeat_interleave(b_loc)))
     ok = (torch.allclose(A, Z @ Z.T) and torch.allclose(B, X @ Z.T) and int(cnt) == N
-          and gathered == [bytes([r]) * 4 for r in range(world)])
+          and gathered == [bytes([r]) * 4 for r in range(world)] and ok_mb)
     out[rank] = bool(ok)
     dist.destroy_process_group()
 
 
-def test_world_size_2_gloo_sharding_and_suffstat_allreduce():
+def test_world_size_2_gloo_sharding_allreduce_and_minibatch_gather():
     import torch.multiprocessing as mp
     mgr = mp.Manager()
     out = mgr.dict()

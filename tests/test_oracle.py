@@ -169,6 +169,20 @@ def test_batch_omp_agrees_with_independent_solvers():
     assert np.max(np.abs(Z - Zs)) <= 1e-12
 
 
+def test_omp_and_soft_thresholding_oracle_match_golden(golden):
+    """the restated `omp` (sparse_coding.py:19-66) and soft_thresholding (feature_encoding.py:26-37) against the outputs
+    of the live reference (tests/golden/omp.npz, oracle/gen_golden.py::gen_omp): both stopping rules, a dictionary that
+    is NOT unit norm (omp solves the true normal equations), and the dispatch through sparse_encoder('omp')"""
+    g = golden("omp")
+    X, D, Ds = g["X"].astype(float), g["D"].astype(float), g["D_scaled"].astype(float)
+    for tag, params, Dd in (("k5", {"n_nonzero_coefs": 5}, D), ("tol1p2", {"tol": 1.2}, D), ("tol0p8", {"tol": 0.8}, D),
+                            ("scaled_k4", {"n_nonzero_coefs": 4}, Ds)):
+        Z = lo.sparse_encoder("omp", params, verbose=False).encode(X, Dd)
+        assert np.array_equal(Z.astype(np.float32), g["Z_" + tag]), tag
+    assert np.array_equal(lo.soft_thresholding(D.T @ X, n_nonzero_coefs=7).astype(np.float32), g["Z_soft_k7"])
+    assert np.array_equal(lo.feature_encoder("soft_thresholding", {"n_nonzero_coefs": 7}).encode(X, D).astype(np.float32), g["Z_soft_k7"])
+
+
 def test_batches_and_quirks():
     assert [len(r) for r in lo.gen_even_batches(250, 100)] == [2] * 99 + [52]
     assert [len(r) for r in lo.gen_even_batches(50, 100)] == [0] * 99 + [50]      # quirk Q8
