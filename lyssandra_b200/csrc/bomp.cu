@@ -3,6 +3,10 @@
 // sparse_encoder.encode(X_numpy, D_numpy).
 #include "common.cuh"
 #include <mutex>
+#include <atomic>
+#include <thread>
+#include <chrono>
+#include <emmintrin.h>
 #include <vector>
 #include <algorithm>
 #include <cstdlib>
@@ -309,10 +313,10 @@ extern "C" int lys_codes_to_dense(const int32_t* idx, const float* val, int64_t 
 // --------------------------------------------------------------------------- host pipeline
 namespace {
 
-// One pipeline per device: staging buffers, two copy/compute streams and the "dictionary ready" event are created
-// once and reused.  Each pipeline has its own lock, so sparse_encoder(n_jobs=G).encode(numpy) — one host thread per
-// GPU (lyssa/utils/__init__.py:92-146 forks one worker per job) — drives G devices concurrently; two callers that
-// target the SAME device take turns.
+// One pipeline per device: staging buffers, two copy/compute streams and events are created once and reused.  Each
+// pipeline has its own lock, so sparse_encoder(n_jobs=G).encode(numpy) — one host thread per GPU
+// (lyssa/utils/__init__.py:92-146 forks one worker per job) — drives G devices concurrently; two callers that target the
+// SAME device take turns.
 struct HostPipe {
     std::mutex mu;
     bool ready = false;
@@ -320,12 +324,15 @@ struct HostPipe {
     unsigned char* base = nullptr;
     cudaStream_t streams[2] = {nullptr, nullptr};
     cudaEvent_t dict_ready = nullptr;
+    size_t stage_bytes = 0;                  // pinned host staging for the sparse codes of one call
+    unsigned char* stage = nullptr;
+    std::vector<cudaEvent_t> chunk_done;     // one event per chunk, grow-only
 };
 constexpr int kMaxDevices = 64;
 HostPipe g_pipes[kMaxDevices];
 
 // caller holds p.mu and has made `device` current
-int pipe_reserve(HostPipe& p, size_t bytes)
+int pipe_reserve(HostPipe& p, size_t bytes, size_t stage_bytes, size_t n_events)
 {
     if (!p.ready) {
         for (int s = 0; s < 2; ++s) LYS_CUDA(cudaStreamCreateWithFlags(&p.streams[s], cudaStreamNonBlocking));
@@ -336,6 +343,16 @@ int pipe_reserve(HostPipe& p, size_t bytes)
         if (p.base) { LYS_CUDA(cudaFree(p.base)); p.base = nullptr; p.bytes = 0; }
         LYS_CUDA(cudaMalloc(&p.base, bytes));
         p.bytes = bytes;
+    }
+    if (p.stage_bytes < stage_bytes) {
+        if (p.stage) { LYS_CUDA(cudaFreeHost(p.stage)); p.stage = nullptr; p.stage_bytes = 0; }
+        LYS_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&p.stage), stage_bytes, cudaHostAllocDefault));
+        p.stage_bytes = stage_bytes;
+    }
+    while (p.chunk_done.size() < n_events) {
+        cudaEvent_t ev;
+        LYS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        p.chunk_done.push_back(ev);
     }
     return LYS_OK;
 }
@@ -356,6 +373,56 @@ int pipe_fail(HostPipe& p, int rc)
             return pipe_fail(pipe, LYS_ECUDA);                                               \
         }                                                                                    \
     } while (0)
+
+// Dense rows on the HOST.  The reference's contract returns the dense (K x N) code matrix, 99.5 % zeros at cfg2: sending
+// it over PCIe costs 4.3 GB per million patches.  Instead the device returns the sparse codes (46 MB) and host threads of
+// this library write the rows of Z — the zero-fill + scatter `Z[Dx, i] = z` of sparse_coding.py:308,:365 and
+// utils/__init__.py:69,89, nothing numerical — chunk by chunk while the device encodes the next chunks: a row is composed
+// in a cache-resident scratch (zeros + its k coefficients) and leaves with non-temporal 16-byte stores, so every byte of Z
+// is written once and never read.
+struct DensifyJob {
+    const int32_t* idx; const float* val;      // (N, k) pinned staging
+    float* Z; int64_t zss; int K, k;
+    int64_t chunk, N;
+    std::atomic<int64_t> ready{0};             // chunks whose codes have landed
+    std::atomic<bool> abort{false};
+};
+
+void densify_worker(DensifyJob* job, int w, int T)
+{
+    const int K = job->K, k = job->k;
+    std::vector<float> scratch_v((size_t)K + 16, 0.f);
+    float* scratch = scratch_v.data();
+    while ((reinterpret_cast<uintptr_t>(scratch) & 15) != 0) ++scratch;
+    const int64_t n_chunks = (job->N + job->chunk - 1) / job->chunk;
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        while (job->ready.load(std::memory_order_acquire) <= c) {
+            if (job->abort.load(std::memory_order_relaxed)) return;
+            std::this_thread::sleep_for(std::chrono::microseconds(20));
+        }
+        const int64_t c0 = c * job->chunk, C = std::min(job->chunk, job->N - c0);
+        const int64_t r0 = c0 + C * w / T, r1 = c0 + C * (w + 1) / T;
+        for (int64_t i = r0; i < r1; ++i) {
+            const int32_t* ii = job->idx + i * k;
+            const float* vv = job->val + i * k;
+            for (int j = 0; j < k; ++j) if (ii[j] >= 0 && ii[j] < K) scratch[ii[j]] = vv[j];
+            float* row = job->Z + i * job->zss;
+            if (((reinterpret_cast<uintptr_t>(row) & 15) == 0) && (K % 4) == 0) {
+                for (int c4 = 0; c4 < K; c4 += 4) _mm_stream_ps(row + c4, _mm_load_ps(scratch + c4));
+            } else {
+                memcpy(row, scratch, sizeof(float) * (size_t)K);
+            }
+            for (int j = 0; j < k; ++j) if (ii[j] >= 0 && ii[j] < K) scratch[ii[j]] = 0.f;
+        }
+    }
+    _mm_sfence();
+}
+
+int host_threads()
+{
+    const unsigned hw = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(16u, hw > 1 ? hw - 1 : 1u));
+}
 
 }  // namespace
 
@@ -380,15 +447,21 @@ extern "C" int lys_bomp_encode_host(const float* X, int64_t xfs, int64_t xss,
     HostPipe& pipe = g_pipes[device];
     std::lock_guard<std::mutex> lock(pipe.mu);
 
+    const bool x_sig_major = (xfs == 1);
+    const bool z_sig_major = (zas == 1);
+    const bool host_dense = Z && z_sig_major;         // rows of Z written by host threads from the sparse codes
+    const bool dev_dense = Z && !z_sig_major;         // atom-major Z: dense block from the device (strided host scatter would thrash)
     const int64_t chunk = std::min<int64_t>(N, 32768);
+    const int64_t n_chunks = (N + chunk - 1) / chunk;
     const size_t ws_bytes = align_up(lys_bomp_workspace_bytes(n, K, chunk, k), 256);
     const size_t d_bytes = align_up((size_t)n * K * 4, 256), g_bytes = align_up((size_t)K * K * 4, 256);
     const size_t x_bytes = align_up((size_t)chunk * n * 4, 256);
     const size_t i_bytes = align_up((size_t)chunk * k * 4, 256);
     const size_t s_bytes = align_up((size_t)chunk * 4, 256);
-    const size_t z_bytes = Z ? align_up((size_t)chunk * K * 4, 256) : 0;
+    const size_t z_bytes = dev_dense ? align_up((size_t)chunk * K * 4, 256) : 0;
     const size_t slot_bytes = x_bytes + 2 * i_bytes + s_bytes + z_bytes + ws_bytes;
-    int rc = pipe_reserve(pipe, d_bytes + g_bytes + 2 * slot_bytes);
+    const size_t codes_bytes = align_up((size_t)N * k * 4, 256);
+    int rc = pipe_reserve(pipe, d_bytes + g_bytes + 2 * slot_bytes, host_dense ? 2 * codes_bytes : 0, (size_t)n_chunks);
     if (rc) return rc;
 
     unsigned char* p = pipe.base;
@@ -400,9 +473,12 @@ extern "C" int lys_bomp_encode_host(const float* X, int64_t xfs, int64_t xss,
         slot[s].idx = reinterpret_cast<int32_t*>(p); p += i_bytes;
         slot[s].val = reinterpret_cast<float*>(p); p += i_bytes;
         slot[s].nsel = reinterpret_cast<int32_t*>(p); p += s_bytes;
-        slot[s].z = Z ? reinterpret_cast<float*>(p) : nullptr; p += z_bytes;
+        slot[s].z = dev_dense ? reinterpret_cast<float*>(p) : nullptr; p += z_bytes;
         slot[s].ws = p; p += ws_bytes;
     }
+    int32_t* st_idx = host_dense ? reinterpret_cast<int32_t*>(pipe.stage) : nullptr;
+    float* st_val = host_dense ? reinterpret_cast<float*>(pipe.stage + codes_bytes) : nullptr;
+
     cudaStream_t s0 = pipe.streams[0], s1 = pipe.streams[1];
     LYS_PIPE_CUDA(pipe, cudaMemcpy2DAsync(dD, (size_t)K * 4, D, (size_t)ldd * 4, (size_t)K * 4, n, cudaMemcpyHostToDevice, s0));
     rc = lys_gram(dD, K, n, K, dG, s0);
@@ -410,38 +486,68 @@ extern "C" int lys_bomp_encode_host(const float* X, int64_t xfs, int64_t xss,
     LYS_PIPE_CUDA(pipe, cudaEventRecord(pipe.dict_ready, s0));
     LYS_PIPE_CUDA(pipe, cudaStreamWaitEvent(s1, pipe.dict_ready, 0));
 
-    const bool x_sig_major = (xfs == 1);
-    const bool z_sig_major = (zas == 1);
+    DensifyJob job;
+    std::vector<std::thread> workers;
+    if (host_dense) {
+        job.idx = st_idx; job.val = st_val; job.Z = Z; job.zss = zss; job.K = K; job.k = k; job.chunk = chunk; job.N = N;
+        const int T = host_threads();
+        for (int w = 0; w < T; ++w) workers.emplace_back(densify_worker, &job, w, T);
+    }
+    auto stop_workers = [&](bool abort) {
+        if (abort) job.abort.store(true);
+        for (auto& t : workers) t.join();
+        workers.clear();
+    };
+
     int which = 0;
-    for (int64_t c0 = 0; c0 < N; c0 += chunk, which ^= 1) {
+    int64_t issued = 0;
+    for (int64_t c0 = 0; c0 < N; c0 += chunk, which ^= 1, ++issued) {
         const int64_t C = std::min(chunk, N - c0);
         cudaStream_t st = pipe.streams[which];
         Slot& sl = slot[which];
         int64_t dxfs, dxss;
+        cudaError_t e;
         if (x_sig_major) {       // host rows of n floats, row stride xss -> device (C, n)
-            LYS_PIPE_CUDA(pipe, cudaMemcpy2DAsync(sl.x, (size_t)n * 4, X + c0 * xss, (size_t)xss * 4, (size_t)n * 4, C,
-                                                  cudaMemcpyHostToDevice, st));
+            e = cudaMemcpy2DAsync(sl.x, (size_t)n * 4, X + c0 * xss, (size_t)xss * 4, (size_t)n * 4, C, cudaMemcpyHostToDevice, st);
             dxfs = 1; dxss = n;
         } else {                 // host (n, N) feature-major -> device (n, C)
-            LYS_PIPE_CUDA(pipe, cudaMemcpy2DAsync(sl.x, (size_t)C * 4, X + c0, (size_t)xfs * 4, (size_t)C * 4, n,
-                                                  cudaMemcpyHostToDevice, st));
+            e = cudaMemcpy2DAsync(sl.x, (size_t)C * 4, X + c0, (size_t)xfs * 4, (size_t)C * 4, n, cudaMemcpyHostToDevice, st);
             dxfs = C; dxss = 1;
         }
-        int64_t dzas = z_sig_major ? 1 : C, dzss = z_sig_major ? K : 1;
-        rc = lys_bomp_encode(sl.x, dxfs, dxss, dD, K, dG, n, K, C, k, sl.idx, sl.val, sl.nsel,
-                             sl.z, dzas, dzss, sl.ws, ws_bytes, st);
-        if (rc) return pipe_fail(pipe, rc);
-        if (idx) LYS_PIPE_CUDA(pipe, cudaMemcpyAsync(idx + c0 * k, sl.idx, (size_t)C * k * 4, cudaMemcpyDeviceToHost, st));
-        if (val) LYS_PIPE_CUDA(pipe, cudaMemcpyAsync(val + c0 * k, sl.val, (size_t)C * k * 4, cudaMemcpyDeviceToHost, st));
-        if (nsel) LYS_PIPE_CUDA(pipe, cudaMemcpyAsync(nsel + c0, sl.nsel, (size_t)C * 4, cudaMemcpyDeviceToHost, st));
-        if (Z) {
-            if (z_sig_major)
-                LYS_PIPE_CUDA(pipe, cudaMemcpy2DAsync(Z + c0 * zss, (size_t)zss * 4, sl.z, (size_t)K * 4, (size_t)K * 4, C,
-                                                      cudaMemcpyDeviceToHost, st));
-            else
-                LYS_PIPE_CUDA(pipe, cudaMemcpy2DAsync(Z + c0, (size_t)zas * 4, sl.z, (size_t)C * 4, (size_t)C * 4, K,
-                                                      cudaMemcpyDeviceToHost, st));
+        rc = (e == cudaSuccess) ? LYS_OK : LYS_ECUDA;
+        if (!rc) rc = lys_bomp_encode(sl.x, dxfs, dxss, dD, K, dG, n, K, C, k, sl.idx, sl.val, sl.nsel,
+                                      sl.z, C, 1, sl.ws, ws_bytes, st);
+        if (!rc && host_dense) {
+            if (cudaMemcpyAsync(st_idx + c0 * k, sl.idx, (size_t)C * k * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                cudaMemcpyAsync(st_val + c0 * k, sl.val, (size_t)C * k * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = LYS_ECUDA;
         }
+        if (!rc && !host_dense) {
+            if (idx && cudaMemcpyAsync(idx + c0 * k, sl.idx, (size_t)C * k * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = LYS_ECUDA;
+            if (val && cudaMemcpyAsync(val + c0 * k, sl.val, (size_t)C * k * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = LYS_ECUDA;
+        }
+        if (!rc && nsel && cudaMemcpyAsync(nsel + c0, sl.nsel, (size_t)C * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = LYS_ECUDA;
+        if (!rc && dev_dense &&
+            cudaMemcpy2DAsync(Z + c0, (size_t)zas * 4, sl.z, (size_t)C * 4, (size_t)C * 4, K, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = LYS_ECUDA;
+        if (!rc && cudaEventRecord(pipe.chunk_done[issued], st) != cudaSuccess) rc = LYS_ECUDA;
+        if (rc) {
+            if (rc == LYS_ECUDA) set_error("lys_bomp_encode_host: a copy or launch of chunk %lld failed: %s", (long long)issued, cudaGetErrorString(cudaGetLastError()));
+            stop_workers(true);
+            return pipe_fail(pipe, rc);
+        }
+        // hand finished chunks to the host threads while later chunks are still being issued (two chunks stay in flight)
+        if (host_dense && issued >= 2) {
+            if (cudaEventSynchronize(pipe.chunk_done[issued - 2]) != cudaSuccess) { stop_workers(true); set_error("lys_bomp_encode_host: chunk failed"); return pipe_fail(pipe, LYS_ECUDA); }
+            job.ready.store(issued - 1, std::memory_order_release);
+        }
+    }
+    if (host_dense) {
+        for (int64_t c = std::max<int64_t>(0, issued - 2); c < issued; ++c) {
+            if (cudaEventSynchronize(pipe.chunk_done[c]) != cudaSuccess) { stop_workers(true); set_error("lys_bomp_encode_host: chunk failed"); return pipe_fail(pipe, LYS_ECUDA); }
+            job.ready.store(c + 1, std::memory_order_release);
+        }
+        stop_workers(false);
+        if (idx) memcpy(idx, st_idx, (size_t)N * k * 4);
+        if (val) memcpy(val, st_val, (size_t)N * k * 4);
     }
     LYS_PIPE_CUDA(pipe, cudaStreamSynchronize(s0));
     LYS_PIPE_CUDA(pipe, cudaStreamSynchronize(s1));
