@@ -411,9 +411,9 @@ ksvd_sweep_kernel(const SweepArgs a)
     set_stage2(a, set2.ent, set2.x, set2.lk);
     set2.xp = 0.f;
     int ent3 = set_stage1(a, make_range<CW>(lo3, hi3, warp, U), lane);
-    float rvC[U][NPL], rvN[U][NPL];
-    load_rows<NPL, U>(a, setC, rgC.nu, lane, rvC);
-    publish_atom<NPL, U, CW>(a, 0, setC, rgC, rvC, red, fx, tid, lane, warp);
+    float rvA[U][NPL], rvB[U][NPL];
+    load_rows<NPL, U>(a, setC, rgC.nu, lane, rvA);
+    publish_atom<NPL, U, CW>(a, 0, setC, rgC, rvA, red, fx, tid, lane, warp);
     compute_sync<CW>();                           // `red` is rewritten by the first look-ahead below
 
     float dold[NPL], doldN[NPL], dnP[NPL], doldP[NPL];
@@ -429,7 +429,9 @@ ksvd_sweep_kernel(const SweepArgs a)
 #ifdef LYS_BRINGUP
     long long t_lap = clock64();
 #endif
-    for (int c = 0; c < K; ++c) {
+    // one atom; the rows of atom c are in `rvC`, those of the look-ahead atom c+1 are loaded into `rvN`.  The caller
+    // alternates the two register arrays instead of copying one into the other (64 moves per atom and warp)
+    auto atom_step = [&](const int c, float (&rvC)[U][NPL], float (&rvN)[U][NPL]) {
         if (tid == 0) *reinterpret_cast<volatile int*>(&s_progress) = c;
         // ---- rows of the look-ahead atom c+1 first: their latency covers everything up to the sums below
         if (c + 1 < K) load_rows<NPL, U>(a, setN, rgN.nu, lane, rvN);
@@ -581,19 +583,19 @@ ksvd_sweep_kernel(const SweepArgs a)
         // rows / coefficients of this CTA's signals are re-read by other warps of THIS CTA only
         compute_sync<CW>();
         LYS_SW_LAP(6);
-        // ---- rotate the pipeline
+        // ---- rotate the pipeline (the row buffers swap roles in the caller)
         gP = g;
 #pragma unroll
         for (int q = 0; q < NPL; ++q) { dnP[q] = dn[q]; doldP[q] = dold[q]; dold[q] = doldN[q]; }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int q = 0; q < NPL; ++q) rvC[u][q] = rvN[u][q];
         setC = setN; rgC = rgN;
         setN = set2; setN.xp = xp2; rgN = make_range<CW>(lo2, hi2, warp, U);
         set2.ent = ent3; set2.x = x3; set2.lk = lk3;
         ent3 = ent4;
         lo2 = lo3; hi2 = hi3; lo3 = lo4; hi3 = hi4; lo4 = lo5; hi4 = hi5;
+    };
+    for (int c = 0; c < K; c += 2) {
+        atom_step(c, rvA, rvB);
+        if (c + 1 < K) atom_step(c + 1, rvB, rvA);
     }
 }
 
