@@ -53,6 +53,7 @@ extern "C" {
 /* ---- library ------------------------------------------------------------------------ */
 LYS_API int         lys_version(void);                 /* 10000*major + 100*minor + patch */
 LYS_API const char* lys_last_error(void);
+LYS_API const char* lys_build_fingerprint(void);   /* hash of the sources the library was built from (loader's staleness check) */
 /* SM count / compute capability of `device`; fails unless it is an sm_100 part. */
 LYS_API int         lys_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
 

@@ -13,7 +13,6 @@ import sys
 _PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "liblyssa_b200.so")
-_STAMP = os.path.join(_PKG, "csrc", ".build_stamp")
 
 SOURCES = ["runtime.cu", "gemm.cu", "bomp_generic.cu", "bomp_fast.cu", "corr_gemm_tc.cu", "bomp_fused.cu", "bomp.cu", "ksvd.cu", "ksvd_sweep.cu", "ksvd_exact.cu", "odl.cu", "odl_gemm_tc.cu", "comm.cu", "spm.cu", "dsift.cu", "thresh.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -28,11 +27,13 @@ def _nvcc():
 
 
 def _fingerprint():
+    """Hash of the sources + flags.  runtime.cu is compiled with -DLYS_FINGERPRINT=<this>, so the library itself says
+    what it was built from (lys_build_fingerprint); no side file has to travel with it."""
     h = hashlib.sha256()
     files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
     files.append(os.path.join(os.path.dirname(_PKG), "include", "lyssa_b200.h"))
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.basename(f).encode())      # names, not absolute paths: the tree is built here and run elsewhere
         with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
@@ -48,23 +49,39 @@ def build(force: bool = False, verbose: bool = False, bringup: bool = False, var
         flags = list(defines) + (["-DLYS_BRINGUP"] if bringup else [])
         return _build_to(os.path.join(_PKG, "liblyssa_b200_%s.so" % name), os.path.join(_PKG, "build_%s" % name), flags, verbose)
     fp = _fingerprint()
-    if not force and os.path.isfile(LIB_PATH) and os.path.isfile(_STAMP):
-        with open(_STAMP) as fh:
-            if fh.read().strip() == fp:
-                return LIB_PATH
-    _build_to(LIB_PATH, os.path.join(_PKG, "build"), [], verbose)
-    with open(_STAMP, "w") as fh:
-        fh.write(fp)
+
+    def fresh():
+        if not os.path.isfile(LIB_PATH):
+            return False
+        with open(LIB_PATH, "rb") as fh:                 # read, not dlopen: a stale handle would be cached by the loader
+            return ("LYSFP:" + fp).encode() in fh.read()
+
+    if not force and fresh():
+        return LIB_PATH
+    # one builder at a time (the ranks of a torchrun launch all arrive here); the others wait on the lock and then
+    # find a fresh library.  The .so is linked under a temporary name and renamed, so a reader never sees half a file.
+    import fcntl
+    with open(os.path.join(_PKG, ".build_lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or not fresh():
+                tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+                _build_to(tmp, os.path.join(_PKG, "build"), [], verbose, fingerprint=fp)
+                os.replace(tmp, LIB_PATH)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
-def _build_to(lib_path, objdir, extra_flags, verbose):
+def _build_to(lib_path, objdir, extra_flags, verbose, fingerprint=None):
     nvcc = _nvcc()
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         cmd = [nvcc] + NVCC_FLAGS + extra_flags + ["-c", os.path.join(CSRC, src), "-o", obj]
+        if fingerprint and src == "runtime.cu":
+            cmd.insert(1, '-DLYS_FINGERPRINT="%s"' % fingerprint)
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

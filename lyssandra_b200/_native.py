@@ -20,6 +20,7 @@ COMM_HANDLE_BYTES = 64
 SIGNATURES = {
     "lys_version": (c_int, []),
     "lys_last_error": (ctypes.c_char_p, []),
+    "lys_build_fingerprint": (ctypes.c_char_p, []),
     "lys_device_info": (c_int, [c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "lys_bomp_launch_count": (c_int, [c_int, c_int, c_i64, c_int]),
     "lys_profile_enable": (c_int, [c_int]),

@@ -200,7 +200,8 @@ __device__ __forceinline__ int argmax_finish_r(const ArgmaxStateR& am, float* s2
 // |tensor-core value - exact correlation| of this residual against any atom, in the accumulator's units
 // (both operands scaled): ||rs - rn16(rs)|| max||d~|| + ||rs|| (max||d - d~|| + gamma max||d~||), slightly inflated.
 template <bool SCREEN>
-__device__ __forceinline__ float store_planes(unsigned char* slotA, int row, const float (&r)[NF], float d_err, float d_max)
+__device__ __forceinline__ float store_planes(unsigned char* slotA, int row, const float (&r)[NF], float d_err, float d_max,
+                                              float* inv_scale = nullptr)
 {
     float t[22];
 #pragma unroll
@@ -212,6 +213,7 @@ __device__ __forceinline__ float store_planes(unsigned char* slotA, int row, con
     int es = 258 - (int)(__float_as_uint(amax) >> 23);
     es = min(max(es, 1), 254);
     const float s = __uint_as_float((uint32_t)es << 23);
+    if (inv_scale) *inv_scale = (es < 254) ? __uint_as_float((uint32_t)(254 - es) << 23) : __uint_as_float(0x00400000u);   // 1/s, exact
     float rho2 = 0.f, drho2 = 0.f;
 #pragma unroll
     for (int kc = 0; kc < NF / 8; ++kc) {
@@ -261,20 +263,78 @@ template <int KNZ> __device__ __forceinline__ void topk_insert(TopK<KNZ>& tk, fl
         tk.c[m - 1] = sw ? cb : ca; tk.c[m] = sw ? ca : cb;
     }
 }
-// VOTE: the branch around the insertion is warp-uniform (taken when any lane inserts) and the insertion itself is
-// predicated: a lane that does not insert bubbles its own k-th entry, which is a no-op on a sorted list.
-// Measured 1.74 ms per 1M signals against 1.89 ms for a per-lane divergent branch (K = 1024, k = 5); same output.
-template <int KNZ, bool VOTE> __device__ __forceinline__ void scan_piece_topk(const uint32_t (&r)[32], int piece, TopK<KNZ>& tk)
+// 'thresh' scan in two passes per 256-column chunk while it sits in tensor memory (round 2; the one-pass running
+// top-k insertion cost 55 cycles per column and warp: with 32 signals per warp some lane inserts at 40 % of the columns).
+// Pass A: the maximum of every (sub-)piece goes into a sorted list of the KNZ largest (sub-)piece maxima; its k-th
+// entry t is a lower bound on the k-th largest correlation of the signal (k distinct columns reach it).  Pass B reads
+// the chunk again and appends every column with v >= t to the signal's candidate list (values are the fp32-faithful
+// tensor-core correlations): ~12 candidates per signal at K = 1024, k = 5, one predicated store pair per column.  The
+// list lives in an L2-resident scratch ([entry][signal], only its owner thread touches it); when a lane holds more
+// than TCAP - 64 entries the warp prunes its lists to their top KNZ (same routine as the final selection), so any
+// input — sorted, constant — stays exact.  Ties: candidates arrive in ascending column order and only a strictly
+// larger value displaces an entry, so equal values keep the lower column.
+#ifndef LYS_THRESH_PREFETCH
+#define LYS_THRESH_PREFETCH 0
+#endif
+constexpr int TCAP = 96;                 // entries per candidate list (pruned above 32; two pieces = 64 columns between checks)
+template <int KNZ> __device__ __forceinline__ void pmx_insert(float (&pmx)[KNZ], float m)
+{
+    float v = (m == m) ? m : -INFINITY;              // a piece of NaNs must not duplicate an entry
+#pragma unroll
+    for (int q = 0; q < KNZ; ++q) {
+        const float hi = fmaxf(pmx[q], v);
+        v = fminf(pmx[q], v);
+        pmx[q] = hi;
+    }
+}
+// SUB = 32: one maximum per piece; SUB = 16 (KNZ > 8: the first chunk's 8 pieces would not give k maxima): two
+template <int KNZ> __device__ __forceinline__ void scan_piece_max(const uint32_t (&r)[32], float (&pmx)[KNZ])
+{
+    if constexpr (KNZ > 8) {
+        float a[16], b[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[16 + i]); }
+        pmx_insert(pmx, Tree3<16>::vmax(a));
+        pmx_insert(pmx, Tree3<16>::vmax(b));
+    } else {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        pmx_insert(pmx, Tree3<32>::vmax(v));
+    }
+}
+// append the columns of one piece that reach t; off = entries held * TM
+__device__ __forceinline__ void scan_piece_collect(const uint32_t (&r)[32], int col0, float t, float* lv, int* lc, uint32_t& off)
 {
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
         const float v = __uint_as_float(r[i]);
-        const bool ins = v > tk.t[KNZ - 1];
-        if constexpr (VOTE) {
-            if (__any_sync(0xffffffffu, ins)) topk_insert(tk, ins ? v : tk.t[KNZ - 1], ins ? piece * 32 + i : tk.c[KNZ - 1]);
-        } else {
-            if (ins) topk_insert(tk, v, piece * 32 + i);
+        if (v >= t) {
+            lv[off] = v;
+            lc[off] = col0 + i;
+            off += TM;
         }
+    }
+}
+// top KNZ of a candidate list, descending, ties to the earlier entry (= lower column)
+template <int KNZ> __device__ __forceinline__ void list_topk(TopK<KNZ>& tk, const float* lv, const int* lc, uint32_t off)
+{
+#pragma unroll
+    for (int m = 0; m < KNZ; ++m) { tk.t[m] = -INFINITY; tk.c[m] = -1; }
+    const uint32_t mx = __reduce_max_sync(0xffffffffu, off);
+#pragma unroll 1
+    for (uint32_t e = 0; e < mx; e += 8 * TM) {              // 16 loads in flight per L2 round trip
+        float v[8];
+        int c[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const bool in = e + q * TM < off;
+            v[q] = in ? lv[e + q * TM] : -INFINITY;
+            c[q] = in ? lc[e + q * TM] : -1;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (v[q] > tk.t[KNZ - 1]) topk_insert(tk, v[q], c[q]);
     }
 }
 
@@ -492,7 +552,7 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
     const uint32_t bar_lead = mapa(bar_local, 0);
     
     if (warp >= 4 * NS) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");       // 256 x 232 + 128 x 40 = 384 x 168: the CTA's allocation, no more
         if (warp == 4 * NS) {
             // ------------------------------------------------------------------- MMA issuer
             if (rank == 0 && lane == 0) {
@@ -503,6 +563,46 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                 PhaseTimer<TIMING> pt;
                 pt.start();
                 uint32_t u = 0;
+                if constexpr (MODE == 1) {
+                    // 'thresh': one pass per tile and the scan, not the tensor pipe, is what a tile waits for.  Each slot
+                    // owns SPS of the TMEM stages and the chunks of the two slots are issued alternately, so both
+                    // slots scan at the same time (issued slot after slot — as Batch-OMP needs it — the second slot
+                    // cannot start before the first one has drained its third chunk: one scanning warp group at a time,
+                    // measured 0.89 ms per 1M signals against 0.5x ms with this order)
+                    constexpr int SPS = NSTG / NS;
+                    for (int r = 0; r < rounds; ++r) {
+#pragma unroll 1
+                        for (int c = 0; c < nch; ++c) {
+#pragma unroll 1
+                            for (int s = 0; s < NS; ++s) {
+                                if (c == 0) {
+                                    mbar_wait(bar_local + 8 * s, (uint32_t)r & 1);            // planes of x landed (both CTAs)
+                                    fence_after();
+                                }
+                                const uint32_t stg = (uint32_t)(s * SPS + (c % SPS));
+                                if (r > 0 || c >= SPS) {                                       // stage drained by its last user
+                                    const int pc = (c >= SPS) ? c - SPS : nch - SPS + c;
+                                    const uint32_t ppar = (c >= SPS) ? ((uint32_t)r & 1) : ((uint32_t)(r - 1) & 1);
+                                    mbar_wait(bar_local + 8 * (24 + 8 * s + pc), ppar);
+                                    fence_after();
+                                }
+                                const uint32_t d_tmem = tmem_base + stg * CH;
+                                const uint32_t a_hi = a_base + s * A_STRIDE, a_lo = a_hi + A_PLANE;
+                                const uint32_t b_hi = b_base + c * B_STRIDE, b_lo = b_hi + GE::B_PLANE;
+#pragma unroll
+                                for (int ks = 0; ks < NF / 16; ++ks)
+                                    mma_f16<PAIR>(d_tmem, make_desc(a_lo + ks * 2 * LBO_A, LBO_A, SBO), make_desc(b_hi + ks * 2 * LBO_B, LBO_B, SBO), kIdesc, ks > 0);
+#pragma unroll
+                                for (int ks = 0; ks < NF / 16; ++ks)
+                                    mma_f16<PAIR>(d_tmem, make_desc(a_hi + ks * 2 * LBO_A, LBO_A, SBO), make_desc(b_lo + ks * 2 * LBO_B, LBO_B, SBO), kIdesc, 1);
+#pragma unroll
+                                for (int ks = 0; ks < NF / 16; ++ks)
+                                    mma_f16<PAIR>(d_tmem, make_desc(a_hi + ks * 2 * LBO_A, LBO_A, SBO), make_desc(b_hi + ks * 2 * LBO_B, LBO_B, SBO), kIdesc, 1);
+                                commit<PAIR>(bar_local + 8 * (8 + 8 * s + c));            // accumulator ready
+                            }
+                        }
+                    }
+                } else
                 for (int r = 0; r < rounds; ++r) {
                     for (int j = 0; j < steps; ++j) {
                         const uint32_t q = (uint32_t)(r * steps + j);
@@ -556,57 +656,65 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
             // mbarrier, tracks how many tiles are ready, so it may lag by any number of tiles.
             const int zs = warp - 4 * NS - 1;
             float* zf = reinterpret_cast<float*>(zbuf + zs * ZB);                  // this slot's row block
-            const uint32_t zsrc = smem_u32(zf);
             volatile uint32_t* ready = tile_ready + zs;
             uint64_t pol;
             asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-            const int zrows = (zss == K) ? min(ZB / (K * 4), 64 / k) : 1;        // rows per bulk store (<= 64 codes)
+            // the 16 KB block works as two halves: while the bulk store of one half reads shared memory the other half
+            // is composed (one block with a wait after every store kept the writer at ~1.2 k cycles per 4 rows — as
+            // long as a whole 'thresh' tile takes the signal warps)
+            constexpr int ZH = ZB / 2;
+            const int zrows = (zss == K) ? min(ZH / (K * 4), 32 / k) : 1;        // rows per bulk store (<= 32 codes: one per lane)
+            // what each half holds from its last store (cleared before the half is composed again)
+            int ha = -1, hb = -1;
+            // lane c handles code c of a group: row c / k, selection slot c % k
+            const int o0 = (lane / k) * K;
             for (int r = 0; r < rounds; ++r) {
                 const int64_t tile = (((int64_t)r * n_units + unit) * PAIR + rank) * NS + zs;
                 const int64_t sig0 = tile * TM;
                 if (tile >= n_tiles) break;
                 while (*ready < 4u * (uint32_t)(r + 1)) __nanosleep(200);        // 4 signal warps per tile
                 __threadfence();
-                const int64_t rows = (N - sig0 < TM) ? (N - sig0) : TM;
-                // lane c (and c + 32) handles code c of a group: row c / k, selection slot c % k (zrows * k <= 64)
-                int a0 = -1, a1 = -1, o0 = 0, o1 = 0;
-                float v0 = 0.f, v1 = 0.f;
-                auto fetch = [&](int64_t g, int& fa0, float& fv0, int& fo0, int& fa1, float& fv1, int& fo1) {
-                    const int nr = (int)((rows - g < zrows) ? (rows - g) : zrows);
-                    fa0 = -1; fa1 = -1;
+                const int rows = (int)((N - sig0 < TM) ? (N - sig0) : TM);
+                auto fetch = [&](int g, int& fa, float& fv) {
+                    const int nr = (rows - g < zrows) ? (rows - g) : zrows;
+                    fa = -1;
                     if (g < rows && lane < nr * k) {
                         const int64_t e = (sig0 + g) * k + lane;
-                        fa0 = __ldcg(idx + e); fv0 = __ldcg(val + e); fo0 = (lane / k) * K;
-                    }
-                    if (g < rows && lane + 32 < nr * k) {
-                        const int64_t e = (sig0 + g) * k + lane + 32;
-                        fa1 = __ldcg(idx + e); fv1 = __ldcg(val + e); fo1 = ((lane + 32) / k) * K;
+                        fa = __ldcg(idx + e); fv = __ldcg(val + e);
                     }
                 };
-                fetch(0, a0, v0, o0, a1, v1, o1);
-                for (int64_t g = 0; g < rows; g += zrows) {
-                    const int nr = (int)((rows - g < zrows) ? (rows - g) : zrows);
-                    if (a0 >= 0) zf[o0 + a0] = v0;
-                    if (a1 >= 0) zf[o1 + a1] = v1;
+                // one group of rows through one half: clear the half's previous coefficients, set the new ones, store
+                auto put = [&](int g, float* zh, int& pa, int a, float v) {
+                    const int nr = (rows - g < zrows) ? (rows - g) : zrows;
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");     // this half's last store has read it
+                    __syncwarp();
+                    if (pa >= 0) zh[o0 + pa] = 0.f;
+                    __syncwarp();
+                    if (a >= 0) zh[o0 + a] = v;
+                    pa = a;
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) {
                         asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-                                     ::"l"(Z + (sig0 + g) * zss), "r"(zsrc), "r"((uint32_t)(nr * K * 4)), "l"(pol) : "memory");
+                                     ::"l"(Z + (sig0 + g) * zss), "r"(smem_u32(zh)), "r"((uint32_t)(nr * K * 4)), "l"(pol) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
-                    int na0, na1, no0 = 0, no1 = 0;
-                    float nv0 = 0.f, nv1 = 0.f;
-                    fetch(g + zrows, na0, nv0, no0, na1, nv1, no1);              // next group's codes while the TMA reads
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the block may be reused
-                    __syncwarp();
-                    if (a0 >= 0) zf[o0 + a0] = 0.f;
-                    if (a1 >= 0) zf[o1 + a1] = 0.f;
-                    __syncwarp();
+                };
+                int a0, b0;
+                float v0 = 0.f, w0 = 0.f;
+                fetch(0, a0, v0);
+                fetch(zrows, b0, w0);
+                for (int g = 0; g < rows; g += 2 * zrows) {
+                    int na, nb;
+                    float nv = 0.f, nw = 0.f;
+                    fetch(g + 2 * zrows, na, nv);                               // two groups ahead: an L2 round trip
+                    fetch(g + 3 * zrows, nb, nw);
+                    put(g, zf, ha, a0, v0);
+                    if (g + zrows < rows) put(g + zrows, zf + ZH / 4, hb, b0, w0);
 #if LYS_ZSLEEP > 0
                     __nanosleep(LYS_ZSLEEP);                                   // spread the tile's 512 KB over its lifetime
 #endif
-                    a0 = na0; v0 = nv0; o0 = no0; a1 = na1; v1 = nv1; o1 = no1;
+                    a0 = na; v0 = nv; b0 = nb; w0 = nw;
                 }
             }
             if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -627,53 +735,80 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
         float* U = scratch + ((size_t)(blockIdx.x * NS + s) * n_keep) * NF * TM + row;
         PhaseTimer<TIMING> pt;
         pt.start();
+        auto load_x = [&](int rr, float (&xr)[NF]) {
+            const int64_t tile_r = (((int64_t)rr * n_units + unit) * PAIR + rank) * NS + s;
+            const int64_t sig_r = tile_r * TM + row;
+            if ((tile_r < n_tiles) && (sig_r < N)) {
+                const float* xp = X + sig_r * xss;
+                if (xfs == 1 && n == NF && ((reinterpret_cast<uintptr_t>(xp) & 15) == 0)) {
+#pragma unroll
+                    for (int q = 0; q < NF / 4; ++q) {
+                        const float4 v4 = __ldg(reinterpret_cast<const float4*>(xp) + q);
+                        xr[4 * q] = v4.x; xr[4 * q + 1] = v4.y; xr[4 * q + 2] = v4.z; xr[4 * q + 3] = v4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) xr[f] = (f < n) ? __ldg(xp + (int64_t)f * xfs) : 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int f = 0; f < NF; ++f) xr[f] = 0.f;
+            }
+        };
         for (int r = 0; r < rounds; ++r) {
             const int64_t tile = (((int64_t)r * n_units + unit) * PAIR + rank) * NS + s;
             const int64_t sig = tile * TM + row;
             const bool live = (tile < n_tiles) && (sig < N);
             // ---- load x, publish its planes (:631 alpha0 = D^T x is step 0 of the loop)
-            if (live) {
-                const float* xp = X + sig * xss;
-                if (xfs == 1 && n == NF && ((reinterpret_cast<uintptr_t>(xp) & 15) == 0)) {
-#pragma unroll
-                    for (int q = 0; q < NF / 4; ++q) {
-                        const float4 v4 = __ldg(reinterpret_cast<const float4*>(xp) + q);
-                        st.r[4 * q] = v4.x; st.r[4 * q + 1] = v4.y; st.r[4 * q + 2] = v4.z; st.r[4 * q + 3] = v4.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int f = 0; f < NF; ++f) st.r[f] = (f < n) ? __ldg(xp + (int64_t)f * xfs) : 0.f;
-                }
-            } else {
-#pragma unroll
-                for (int f = 0; f < NF; ++f) st.r[f] = 0.f;
-            }
-            st.E = store_planes<SCREEN>(slotA, row, st.r, d_err, d_max);
+            if (MODE == 0 || r == 0 || !LYS_THRESH_PREFETCH) load_x(r, st.r);
+            float inv_s = 1.f;
+            st.E = store_planes<SCREEN>(slotA, row, st.r, d_err, d_max, MODE == 1 ? &inv_s : nullptr);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * s);
+            // 'thresh' needs x only for its planes: the next tile's x is loaded now and is in flight during the scan
+            if (MODE == 1 && LYS_THRESH_PREFETCH && r + 1 < rounds) load_x(r + 1, st.r);
             st.cnt = 0;
             st.done = !live;
             pt.lap(0, lane);
             if constexpr (MODE == 1) {
-                TopK<KNZ> tk;
+                float* lv = scratch + ((size_t)(blockIdx.x * NS + s) * 2 * TCAP) * TM + row;     // candidate values [entry][row]
+                int* lc = reinterpret_cast<int*>(lv + (size_t)TCAP * TM);                        // candidate columns
+                uint32_t off = 0u;                                                                // entries held * TM
+                float pmx[KNZ];
 #pragma unroll
-                for (int m = 0; m < KNZ; ++m) { tk.t[m] = -INFINITY; tk.c[m] = -1; }
+                for (int m = 0; m < KNZ; ++m) pmx[m] = -INFINITY;
+                float t_floor = live ? -INFINITY : INFINITY;          // rows past N collect nothing
+                TopK<KNZ> tk;
                 const uint32_t qq = (uint32_t)r;
-                const uint32_t u0 = (qq * NS + s) * (uint32_t)nch;
 #pragma unroll 1
                 for (int c = 0; c < nch; ++c) {
-                    const uint32_t stg = (u0 + c) & (NSTG - 1);
+                    const uint32_t stg = (uint32_t)(s * (NSTG / NS) + (c % (NSTG / NS)));     // this slot's stages (see the issuer)
                     mbar_wait(bar_local + 8 * (8 + 8 * s + c), qq & 1);
                     fence_after();
                     const uint32_t ta = tq + stg * CH;
                     uint32_t b0[32], b1[32];
+                    // ---- pass A: (sub-)piece maxima -> threshold
                     LYS_TMEM_LD_X32(ta, b0);
 #pragma unroll 1
                     for (int sc = 0; sc < NP; sc += 2) {
                         LYS_TMEM_WAIT_X32(b0);
                         LYS_TMEM_LD_X32(ta + (sc + 1) * 32, b1);
-                        scan_piece_topk<KNZ, true>(b0, c * NP + sc, tk);
+                        scan_piece_max<KNZ>(b0, pmx);
+                        LYS_TMEM_WAIT_X32(b1);
+                        LYS_TMEM_LD_X32(ta + ((sc + 2 < NP) ? (sc + 2) * 32 : 0), b0);      // wraps to piece 0 for pass B
+                        scan_piece_max<KNZ>(b1, pmx);
+                    }
+                    float t = pmx[KNZ - 1];
+#pragma unroll
+                    for (int m = 0; m < KNZ - 1; ++m) t = (m == k - 1) ? pmx[m] : t;
+                    t = fmaxf(t, t_floor);
+                    // ---- pass B: candidates of this chunk
+#pragma unroll 1
+                    for (int sc = 0; sc < NP; sc += 2) {
+                        LYS_TMEM_WAIT_X32(b0);
+                        LYS_TMEM_LD_X32(ta + (sc + 1) * 32, b1);
+                        scan_piece_collect(b0, (c * NP + sc) * 32, t, lv, lc, off);
                         LYS_TMEM_WAIT_X32(b1);
                         if (sc + 2 < NP) LYS_TMEM_LD_X32(ta + (sc + 2) * 32, b0);
                         else {
@@ -681,27 +816,35 @@ bomp_tc_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss, int n,
                             __syncwarp();
                             if (lane == 0) mbar_arrive_cluster(bar_lead + 8 * (24 + 8 * s + c));
                         }
-                        scan_piece_topk<KNZ, true>(b1, c * NP + sc + 1, tk);
+                        scan_piece_collect(b1, (c * NP + sc + 1) * 32, t, lv, lc, off);
+                        // a lane close to the capacity: the warp prunes its lists to their top KNZ entries
+                        if (__any_sync(0xffffffffu, off > (uint32_t)((TCAP - 64) * TM))) {
+                            list_topk<KNZ>(tk, lv, lc, off);
+                            off = 0u;
+#pragma unroll
+                            for (int m = 0; m < KNZ; ++m)
+                                if (tk.c[m] >= 0) { lv[off] = tk.t[m]; lc[off] = tk.c[m]; off += TM; }
+                            float tkk = tk.t[KNZ - 1];
+#pragma unroll
+                            for (int m = 0; m < KNZ - 1; ++m) tkk = (m == k - 1) ? tk.t[m] : tkk;
+                            t_floor = fmaxf(t_floor, tkk);
+                            t = fmaxf(t, t_floor);
+                        }
                     }
                 }
+                list_topk<KNZ>(tk, lv, lc, off);
                 if (live) {
-                    // Z = Alpha on the kept entries (:424): the exact fp32 correlation, not the tensor-core ranking value
+                    // Z = Alpha on the kept entries (:424).  The accumulator is the fp32-faithful correlation of the two
+                    // scaled operands (three fp16 products, 22+ mantissa bits each side, fp32 accumulation: the same
+                    // error as an fp32 FMA dot product, tests/test_gpu_gemm.py); both scales are powers of two, so
+                    // undoing them is exact.  (Round 1 recomputed the k kept dots from the fp32 atoms: five 256-byte
+                    // gathers per signal, 28 % of the kernel's stall samples, and x had to stay in registers.)
+                    const float inv_d = 1.f / __ldg(dstats);
 #pragma unroll
                     for (int m = 0; m < KNZ; ++m) {
                         if (m < k) {
-                            const int col = tk.c[m];
-                            float acc = 0.f;
-                            if (col >= 0) {
-                                const float4* dp = reinterpret_cast<const float4*>(Dt + (size_t)col * NF);
-#pragma unroll
-                                for (int q4 = 0; q4 < NF / 4; ++q4) {
-                                    const float4 d4 = __ldg(dp + q4);
-                                    acc = fmaf(d4.x, st.r[4 * q4], acc); acc = fmaf(d4.y, st.r[4 * q4 + 1], acc);
-                                    acc = fmaf(d4.z, st.r[4 * q4 + 2], acc); acc = fmaf(d4.w, st.r[4 * q4 + 3], acc);
-                                }
-                            }
-                            idx[sig * k + m] = col;
-                            val[sig * k + m] = acc;
+                            idx[sig * k + m] = tk.c[m];
+                            val[sig * k + m] = (tk.c[m] >= 0) ? (tk.t[m] * inv_s) * inv_d : 0.f;
                         }
                     }
                     if (nsel) nsel[sig] = k;
@@ -959,6 +1102,9 @@ size_t dt_bytes(int K) { return (size_t)K * NF * sizeof(float); }
 // orthonormalised directions u_0..u_{k-3} of every signal in flight: [CTA][slot][vector][feature][signal]
 size_t scratch_bytes(int k) { return (size_t)sm_count() * MAX_SLOTS * (k > 2 ? k - 2 : 0) * NF * TM * sizeof(float); }
 
+// 'thresh' candidate lists of every signal in flight: [CTA][slot][values | columns][entry][signal]
+size_t thresh_lists_bytes() { return (size_t)sm_count() * MAX_SLOTS * 2 * TCAP * TM * sizeof(float); }
+
 struct FusedWs { unsigned char* planes; float* Dt; float* dstats; float* scratch; };
 FusedWs carve_ws(void* workspace, int K)
 {
@@ -1073,7 +1219,7 @@ int bomp_encode_fused(const float* X, int64_t xfs, int64_t xss, const float* D, 
 size_t thresh_fused_workspace_bytes(int n, int K, int64_t, int k)
 {
     if (!fused_shape_ok(n, K, k)) return 0;
-    return align_up(planes_bytes(K), 256) + align_up(dt_bytes(K), 256) + 256 + 256;
+    return align_up(planes_bytes(K), 256) + align_up(dt_bytes(K), 256) + 256 + align_up(thresh_lists_bytes(), 256) + 256;
 }
 
 // 'thresh' coder through the fused kernel (MODE 1): same shapes and Z layout rules as bomp_encode_fused
@@ -1084,8 +1230,7 @@ int thresh_encode_fused(const float* X, int64_t xfs, int64_t xss, const float* D
     if (!fused_shape_ok(n, K, k)) return LYS_EUNSUPPORTED;
     if (Z && (zas != 1 || (zss % 4) != 0 || (reinterpret_cast<uintptr_t>(Z) & 15) != 0)) return LYS_EUNSUPPORTED;
     if (workspace_bytes < thresh_fused_workspace_bytes(n, K, N, k)) return LYS_EWORKSPACE;
-    FusedWs w = carve_ws(workspace, K);
-    w.scratch = nullptr;
+    const FusedWs w = carve_ws(workspace, K);          // w.scratch: the candidate lists
     const int rc = prepare_dictionary(D, ldd, n, K, w, stream);
     if (rc) return rc;
     return launch_by_shape<1, false>(X, xfs, xss, n, w, nullptr, K, N, k, idx, val, nsel, Z, zss, stream);

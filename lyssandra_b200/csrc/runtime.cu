@@ -33,6 +33,14 @@ extern "C" int lys_version(void) { return 100; }   // 0.1.0
 
 extern "C" const char* lys_last_error(void) { return lys::g_err; }
 
+// fingerprint of the sources this library was built from (set by lyssandra_b200/_build.py; the loader compares it with
+// the tree it runs in, so a stale library is rebuilt instead of being loaded with mismatched signatures)
+#ifndef LYS_FINGERPRINT
+#define LYS_FINGERPRINT "unknown"
+#endif
+static const char g_fingerprint[] = "LYSFP:" LYS_FINGERPRINT;      // the marker lets the loader find it without dlopen
+extern "C" const char* lys_build_fingerprint(void) { return g_fingerprint + 6; }
+
 extern "C" int lys_device_info(int device, int* sm_count, int* cc_major, int* cc_minor)
 {
     int n = 0;

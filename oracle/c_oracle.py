@@ -15,9 +15,21 @@ _SO = os.path.join(_HERE, "_build", "liblyssa_oracle.so")
 _lib = None
 
 
+def _stale():
+    return not os.path.isfile(_SO) or os.path.getmtime(_SO) < os.path.getmtime(os.path.join(_HERE, "bomp_oracle.c"))
+
+
 def build(force=False):
-    if force or not os.path.isfile(_SO) or os.path.getmtime(_SO) < os.path.getmtime(os.path.join(_HERE, "bomp_oracle.c")):
-        subprocess.run(["make", "-C", _HERE, "-B"], check=True, stdout=subprocess.DEVNULL)
+    if force or _stale():
+        import fcntl
+        os.makedirs(os.path.join(_HERE, "_build"), exist_ok=True)
+        with open(os.path.join(_HERE, "_build", ".lock"), "w") as lock:      # the ranks of one launch may all arrive here
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if force or _stale():
+                    subprocess.run(["make", "-C", _HERE, "-B"], check=True, stdout=subprocess.DEVNULL)
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     return _SO
 
 

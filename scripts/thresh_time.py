@@ -13,7 +13,8 @@ for name, fn in (("thresh k=5", lambda: engine.thresh_encode(Xd, Dd, 5)),
                  ("thresh k=5 dense", lambda: engine.thresh_encode(Xd, Dd, 5, dense=True)),
                  ("thresh k=102", lambda: engine.thresh_encode(Xd, Dd, 102)),
                  ("iht k=5 n_iter=4", lambda: engine.iht_encode(Xd, Dd, 5, 0.2, 4)),
-                 ("bomp k=5", lambda: engine.bomp_encode(Xd, Dd, 5))):
+                 ("bomp k=5", lambda: engine.bomp_encode(Xd, Dd, 5)),
+                 ("bomp k=5 dense", lambda: engine.bomp_encode(Xd, Dd, 5, dense=True))):
     for _ in range(2): fn()
     torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)

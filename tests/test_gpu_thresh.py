@@ -77,6 +77,30 @@ def test_thresh_iht_seeded_vs_oracle(n, K, N, alg, params):
     assert isinstance(Zh, np.ndarray) and np.array_equal(Zh, Zd.cpu().numpy())
 
 
+@pytest.mark.parametrize("K,k", [(1024, 5), (512, 10), (256, 3)])
+def test_thresh_fused_candidate_lists_stay_exact_on_sorted_and_constant_correlations(K, k):
+    # the fused kernel collects, per signal, the columns that reach a running lower bound of the k-th largest
+    # correlation and prunes the list when it fills up (bomp_fused.cu, MODE 1).  Correlations that ASCEND with the
+    # column make every column a candidate (the bound always lags), all-equal correlations make every column a tie:
+    # both must still return the k largest with ties to the lower column (sparse_coding.py:416-425).
+    n, N = 64, 300
+    rng = np.random.RandomState(K + k)
+    theta = np.linspace(1.2, 0.1, K)                         # cos(theta) ascends with the column
+    D = np.zeros((n, K), dtype=np.float32)
+    D[0], D[1] = np.cos(theta), np.sin(theta)
+    X = np.zeros((n, N), dtype=np.float32)
+    X[0] = rng.uniform(0.5, 2.0, N)                          # ascending correlations: the last k columns win
+    X[:, 100:200] *= -1.0                                    # descending: the first k columns win
+    X[:, 200:] = 0.0                                         # all correlations equal (0): the first k columns
+    codes = sparse_encoder("thresh", {"n_nonzero_coefs": k}, verbose=False).encode_sparse(
+        torch.as_tensor(np.ascontiguousarray(X), device=DEV), D)
+    idx = codes.idx.cpu().numpy(); val = codes.val.cpu().numpy()
+    A = D.astype(np.float64).T @ X.astype(np.float64)
+    want = np.argsort(-A, axis=0, kind="stable")[:k].T      # descending, ties to the lower column
+    assert np.array_equal(idx, want)
+    assert np.allclose(val, np.take_along_axis(A.T, want, axis=1), rtol=1e-5, atol=1e-6)
+
+
 def test_thresh_keeps_largest_signed_not_absolute():
     # the reference sorts SIGNED correlations (sparse_coding.py:423): a large negative one is never kept
     D = np.eye(4, dtype=np.float32)
