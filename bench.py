@@ -242,6 +242,7 @@ def ksvd_iteration_ms(dev, rank, world, iters=3):
             totals.append(ev[0].elapsed_time(ev[5]))
             stages.append([ev[i].elapsed_time(ev[i + 1]) for i in range(5)])
 
+    _progress("ksvd_iteration: timed iterations done")
     # ---- parity of the sharded sweep against ONE GPU on the same signals (a 262144-patch slice: the first
     # 262144/world patches of every shard, gathered on rank 0 in rank order)
     parity = None
@@ -251,6 +252,7 @@ def ksvd_iteration_ms(dev, rank, world, iters=3):
         Dsh = D0.clone()
         torch.cuda.synchronize(dev); ctx.barrier()
         _, err_sh = iteration(Xs, Dsh, ex.handle)
+        _progress("ksvd_iteration: sharded sweep of the parity slice done")
         mine = Xs.t().contiguous()                                      # (m, n)
         allX = torch.empty((world * m, n), dtype=torch.float32, device=dev)
         dist.all_gather_into_tensor(allX, mine)
@@ -294,6 +296,7 @@ def scspm_images_per_s(dev, rank, world, n_total=10000, size=256, chunk=250):
     enc = sparse_encoder("bomp", {"n_nonzero_coefs": 5}, verbose=False)
     ex = sc_spm_extractor(feature_extractor=dsift_extractor(step_size=6, patch_size=16), levels=(1, 2, 4), sparse_coder=enc,
                           pooling_operator=sc_max_pooling(), normalizer=l2_normalizer())
+    _progress("scspm: images resident")
     F = [ex.encode(blocks[0], D)]
     torch.cuda.synchronize(dev)
     if world > 1:
@@ -304,6 +307,7 @@ def scspm_images_per_s(dev, rank, world, n_total=10000, size=256, chunk=250):
     e1.record()
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
+    _progress("scspm: shard done")
     assert tuple(F[0].shape) == (21 * 1024, chunk) and all(bool(torch.isfinite(f).all()) for f in F)
     parity = None
     if world > 1:
@@ -340,17 +344,22 @@ def odl_minibatch_ms(dev, rank, world, n=128, K=2048, k=5, b=4096, n_mb=24):
 
     def run(Xs, bs, dctx):
         D = D0.clone()
-        torch.cuda.synchronize(dev); ctx.barrier()
+        torch.cuda.synchronize(dev)
+        if dctx is not None:              # the single-GPU reference run is rank 0's alone: no collective in it
+            dctx.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         D, A, B = online_dict_learn(Xs, K, sparse_coder=enc, batch_size=bs, D_init=D, beta=0.9, n_epochs=1, dist=dctx)
         e1.record(); torch.cuda.synchronize(dev)
         return e0.elapsed_time(e1) / n_mb, D, A
 
+    _progress("odl: data resident")
     run(X, b_loc, ctx if world > 1 else None)                                               # warm-up
+    _progress("odl: warm-up epoch done")
     ms, D, A = run(X, b_loc, ctx if world > 1 else None)
     ms2, D_again, _ = run(X, b_loc, ctx if world > 1 else None)
     reproducible = bool(torch.equal(D, D_again))
+    _progress("odl: timed epochs done")
     # stage split of one minibatch (this rank's slice encoded, whole minibatch accumulated)
     def timed(fn):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -368,6 +377,7 @@ def odl_minibatch_ms(dev, rank, world, n=128, K=2048, k=5, b=4096, n_mb=24):
             st["encode_slice"].append(t1); st["accumulate"].append(t2); st["update"].append(t3)
     stages = {key: float(np.median(v)) for key, v in st.items()}
     parity = {"bitwise_reproducible_across_runs": reproducible}
+    _progress("odl: stage split done")
     if world > 1:
         allD = torch.empty((world,) + tuple(D.shape), dtype=torch.float32, device=dev)
         dist.all_gather_into_tensor(allD, D.contiguous())
@@ -401,6 +411,15 @@ def sibling_coders_ms(dev, n=64, K=1024, N=1 << 20, k=5, reps=3):
         torch.cuda.synchronize(dev)
         out[name] = e0.elapsed_time(e1) / reps
     return out
+
+
+_T0 = time.perf_counter()
+
+
+def _progress(msg):
+    """phase marks on stderr (every rank): where a slow or hung run spent its time"""
+    sys.stderr.write("[bench rank %s +%.1fs] %s\n" % (os.environ.get("RANK", "0"), time.perf_counter() - _T0, msg))
+    sys.stderr.flush()
 
 
 # ----------------------------------------------------------------------------- own arm
@@ -437,6 +456,7 @@ def run_own(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _native.load()
     _native.check(lib.lys_device_info(local, None, None, None))
+    _progress("library loaded, process group up")
 
     n, K, k, N = N_FEATURES, N_ATOMS, K_NONZERO, N_PER_GPU
     Xh_sm = np.ascontiguousarray(lo.synthetic_patches(N, n, seed=0 if rank == 0 else 1000 + rank).T)   # (N, n) signal-major; seed 1 is D's
@@ -465,9 +485,11 @@ def run_own(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    _progress("inputs resident")
     for _ in range(max(args.warmup, 3)):
         step()
     sync_all()
+    _progress("warm-up done")
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
@@ -506,6 +528,7 @@ def run_own(args):
         except Exception as exc:
             parity = {"failed": repr(exc)}
 
+    _progress("timed region done: %.3f ms per step" % (ms / args.steps))
     # ---- e2e: host buffers through the C-ABI, copies inside the timed region
     Xpin = torch.from_numpy(Xh_sm).pin_memory()
     Zpin = torch.empty((N, K), dtype=torch.float32).pin_memory()
@@ -516,6 +539,7 @@ def run_own(args):
                                                None, None, None, Zpin.data_ptr(), 1, K, local))
 
     e2e_steps = max(2, min(args.steps, 5))
+    _progress("e2e buffers pinned")
     e2e_step()
     sync_all()
     t0 = time.perf_counter()
@@ -536,43 +560,82 @@ def run_own(args):
                                                ipin.data_ptr(), vpin.data_ptr(), spin.data_ptr(), None, 1, K, local))
     e2e_sparse_s = time.perf_counter() - t0
 
+    _progress("e2e done: %.1f ms per step" % (e2e_s * 1e3 / e2e_steps))
     del Xpin, Zpin, ipin, vpin, spin, Zt
     torch.cuda.empty_cache()
-    ksvd_ms, ksvd_stages, ksvd_note, ksvd_parity = None, None, None, None
-    if not args.no_extras:
-        try:
-            ksvd_ms, ksvd_stages, ksvd_parity = ksvd_iteration_ms(dev, rank, world)
-        except Exception as exc:          # secondary metric: reported, never fatal for the headline line
-            ksvd_ms, ksvd_note = None, "failed: %r" % (exc,)
-
-    spm_ms, spm_note, spm_parity = -1.0, None, None
-    if not args.no_extras:
-        try:
-            spm_ms, spm_parity = scspm_images_per_s(dev, rank, world)
-        except Exception as exc:
-            spm_note = "failed: %r" % (exc,)
-
-    odl_ms, odl_stages, odl_note, odl_parity = -1.0, None, None, None
-    if not args.no_extras:
-        try:
-            odl_ms, odl_stages, odl_parity = odl_minibatch_ms(dev, rank, world)
-        except Exception as exc:
-            odl_note = "failed: %r" % (exc,)
-
-    sib_ms, sib_note = None, None
-    if not args.no_extras and rank == 0:
-        try:
-            sib_ms = sibling_coders_ms(dev)
-        except Exception as exc:
-            sib_note = "failed: %r" % (exc,)
-
-    t = torch.tensor([ms, e2e_s * 1e3 / e2e_steps, e2e_sparse_s * 1e3 / e2e_steps, ksvd_ms if ksvd_ms is not None else -1.0, spm_ms, odl_ms],
-                     dtype=torch.float64, device=dev)
+    # headline numbers: max over ranks, BEFORE the secondary measurements (a stuck extra must not cost the headline line)
+    t = torch.tensor([ms, e2e_s * 1e3 / e2e_steps, e2e_sparse_s * 1e3 / e2e_steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms, e2e_sparse_ms, ksvd_ms_max, spm_ms_max, odl_ms_max = [float(v) for v in t.tolist()]
+    ms_max, e2e_ms, e2e_sparse_ms = [float(v) for v in t.tolist()]
 
-    if rank == 0:
+    # ---- secondary measurements (extras), each finalised (max over ranks) as soon as it is done, under a watchdog:
+    # if they exceed --extras-budget seconds rank 0 prints the line with what is finished and every rank exits 0
+    finished = {}                      # name -> (ms max over ranks, payload of rank 0)
+    state = {"line": None, "done": False}
+    lock = threading.Lock()
+
+    def emit(aborted=None):
+        with lock:
+            if state["done"]:
+                return
+            state["done"] = True
+            if rank == 0 and state["line"] is not None:
+                line = state["line"](finished, aborted)
+                sys.stdout.write(json.dumps(line) + "\n")
+                sys.stdout.flush()
+
+    def watchdog():
+        deadline = time.perf_counter() + float(args.extras_budget)
+        while time.perf_counter() < deadline:
+            time.sleep(0.5)
+            if state["done"]:
+                return
+        _progress("extras exceeded %.0f s: printing the line without the unfinished ones and exiting" % args.extras_budget)
+        emit(aborted="extras exceeded the %.0f s budget; finished: %s" % (args.extras_budget, sorted(finished)))
+        os._exit(0)
+
+    def max_over_ranks(v):
+        tt = torch.tensor([v if v is not None else -1.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def run_extra(name, fn, all_ranks=True):
+        if args.no_extras or (not all_ranks and rank != 0):
+            return
+        payload, note, v = None, None, None
+        try:
+            v, payload = fn()
+        except Exception as exc:          # secondary metric: reported, never fatal for the headline line
+            note = "failed: %r" % (exc,)
+        vmax = max_over_ranks(v) if all_ranks else (v if v is not None else -1.0)
+        finished[name] = (vmax, payload, note)
+        _progress("extras: %s done" % name)
+
+    def _ksvd():
+        v, stages, par = ksvd_iteration_ms(dev, rank, world)
+        return v, (stages, par)
+
+    def _spm():
+        v, par = scspm_images_per_s(dev, rank, world)
+        return v, par
+
+    def _odl():
+        v, stages, par = odl_minibatch_ms(dev, rank, world)
+        return v, (stages, par)
+
+    def _sib():
+        return 0.0, sibling_coders_ms(dev)
+
+
+    def build_line(fin, aborted):
+        ksvd_ms_max, kp, ksvd_note = fin.get("ksvd_iteration", (-1.0, None, "not run"))
+        ksvd_stages, ksvd_parity = kp if kp else (None, None)
+        spm_ms_max, spm_parity, spm_note = fin.get("scspm_pipeline", (-1.0, None, "not run"))
+        odl_ms_max, op, odl_note = fin.get("odl_minibatch", (-1.0, None, "not run"))
+        odl_stages, odl_parity = op if op else (None, None)
+        _, sib_ms, sib_note = fin.get("sibling_coders", (-1.0, None, "not run"))
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -639,10 +702,37 @@ def run_own(args):
                 line["roofline"]["traffic_source"] = tj.get("_source", "ncu capture under profiles/ (not measured in this run)")
             except Exception:
                 pass
-        print(json.dumps(line))
+        if aborted:
+            line["extras"]["aborted"] = aborted
+        return line
+
+    state["line"] = build_line
+    wd = threading.Thread(target=watchdog, daemon=True)
+    if not args.no_extras:
+        wd.start()
+    run_extra("ksvd_iteration", _ksvd)
+    run_extra("scspm_pipeline", _spm)
+    run_extra("odl_minibatch", _odl)
+    run_extra("sibling_coders", _sib, all_ranks=False)
+    emit()
+    _progress("line printed")
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # The result is out; nothing after this point may keep the launch alive.  dist.barrier() with an eagerly
+        # initialised NCCL communicator returns on the host before the peers have arrived, so a rank that had no
+        # rank-0-only extra to run used to tear NCCL down while rank 0 was still measuring, and rank 0 then hung in its
+        # own barrier (seen on the 2- and 4-GPU boxes).  The ranks now meet at an all-reduce whose result the host reads,
+        # bounded by a timer, and leave without the NCCL teardown.
+        threading.Timer(30.0, lambda: os._exit(0)).start()
+        try:
+            fin = torch.ones(1, device=dev)
+            dist.all_reduce(fin)
+            _progress("final rendezvous: %d of %d ranks" % (int(fin.item()), world))
+        except Exception as exc:
+            _progress("final rendezvous failed: %r" % (exc,))
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 
@@ -655,6 +745,7 @@ def main():
     ap.add_argument("--sample", type=int, default=None, help="(reference arm) columns per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary K-SVD iteration timing")
+    ap.add_argument("--extras-budget", type=float, default=240.0, help="seconds the secondary measurements may take before the line is printed without the unfinished ones")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
