@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from .. import engine
-from .utils import init_dictionary
+from .utils import init_dictionary, init_dictionary_sharded, replace_unused_atoms_sharded
 
 
 def approx_ksvd(Y, D, X, n_cycles=1, verbose=True, comm=None):
@@ -79,7 +79,8 @@ def ksvd_dict_learn(X, n_atoms, init_dict="data", sparse_coder=None, max_iter=20
     (distributed.PeerExchange); X is then THIS rank's contiguous shard of the signals, D is
     replicated.  Encode needs no collective; the sweep all-reduces its per-atom sums inside the
     kernel; the error is one scalar all-reduce; 'data' initialisation and unused-atom
-    replacement draw from rank 0's shard and are broadcast."""
+    replacement draw over the GLOBAL column space with rank 0's RNG — the draws a single process
+    holding the concatenated shards would make — and fetch each column from its owner."""
     if max_iter is None or int(max_iter) < 0:
         # the reference's ksvd_coder default (max_iter=None, ksvd.py:240) only "works" on Python 2, where
         # `0 < None` is False and the loop is silently skipped; say what is wrong instead
@@ -97,15 +98,14 @@ def ksvd_dict_learn(X, n_atoms, init_dict="data", sparse_coder=None, max_iter=20
     if multi and comm is None:
         raise ValueError("sharded K-SVD needs a distributed.PeerExchange (exchange=...)")
     unused_data = np.empty((0,), dtype=np.int64)
+    offsets = None
     if isinstance(init_dict, str):
         if init_dict != "data":
             raise NotImplementedError("init_dict must be 'data' or an (n, K) array")
-        if not multi or dist.rank == 0:
-            D, unused_data = init_dictionary(Xd, n_atoms, method="data", return_unused_data=True)   # :151-153
+        if multi:                    # drawn over the global column space, columns fetched from their owners
+            D, unused_data, offsets = init_dictionary_sharded(dist, Xd, n_atoms)
         else:
-            D = torch.empty((Xd.shape[0], n_atoms), dtype=torch.float32, device=dev)
-        if multi:
-            dist.broadcast_(D, src=0)
+            D, unused_data = init_dictionary(Xd, n_atoms, method="data", return_unused_data=True)   # :151-153
     else:
         D = engine.as_dictionary(init_dict, dev).clone()                                        # :155 np.copy
     if mmap:
@@ -124,16 +124,18 @@ def ksvd_dict_learn(X, n_atoms, init_dict="data", sparse_coder=None, max_iter=20
             torch.cuda.synchronize(dev)
         t1 = time.perf_counter()
         D, _, unused_atoms, R = _ksvd_keep_residual(Xd, D, codes, n_cycles=n_cycles, comm=comm, exact=not approx)   # :182-190
-        for slot in unused_atoms:                                                               # :199-207
-            if len(unused_data) == 0 or (multi and dist.rank != 0):
-                break
-            pos = np.random.choice(len(unused_data), size=1)[0]
-            col = int(unused_data[pos])
-            engine.gather_cols_(Xd, [col], D, dst_cols=[slot])
-            engine.norm_cols_(D[:, slot:slot + 1])
-            unused_data = np.delete(unused_data, pos)
-        if multi and len(unused_atoms) > 0:
-            dist.broadcast_(D, src=0)
+        if multi:                                                                               # :199-207, sharded
+            if len(unused_atoms) > 0 and offsets is not None:
+                unused_data = replace_unused_atoms_sharded(dist, Xd, D, unused_atoms, unused_data, offsets)
+        else:
+            for slot in unused_atoms:                                                           # :199-207
+                if len(unused_data) == 0:
+                    break
+                pos = np.random.choice(len(unused_data), size=1)[0]
+                col = int(unused_data[pos])
+                engine.gather_cols_(Xd, [col], D, dst_cols=[slot])
+                engine.norm_cols_(D[:, slot:slot + 1])
+                unused_data = np.delete(unused_data, pos)
         # :220 approx_error(D, Z, X): the atoms replaced above have no users, so the residual the sweep
         # maintained is still X - D Z
         err = engine.frobenius2(R)

@@ -17,7 +17,7 @@ import torch
 
 from .. import engine
 from ..utils import gen_batches
-from .utils import init_dictionary
+from .utils import init_dictionary, init_dictionary_sharded
 
 
 def _gather_minibatch(dist, Xb, codes):
@@ -54,7 +54,10 @@ def online_dict_learn(X, n_atoms, sparse_coder=None, batch_size=None, A=None, B=
     dev = Xd.device
     n_features, n_samples = Xd.shape
     if D_init is None:
-        D, _unused = init_dictionary(Xd, n_atoms, method="data", return_unused_data=True)   # :44-45
+        if dist is not None and dist.world > 1:          # one dictionary for all ranks, drawn over every rank's slice
+            D, _unused, _ = init_dictionary_sharded(dist, Xd, n_atoms)
+        else:
+            D, _unused = init_dictionary(Xd, n_atoms, method="data", return_unused_data=True)   # :44-45
     else:
         D = engine.as_dictionary(D_init, dev)                                      # :47 (no copy)
     batch_idx = gen_batches(n_samples, batch_size=batch_size)                      # :52

@@ -67,6 +67,21 @@ class DistContext(object):
             dist.broadcast(t, src=src, group=self.group)
         return t
 
+    def allgather_object(self, obj):
+        """every rank's (picklable) object, in rank order"""
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def broadcast_object(self, obj, src=0):
+        if self.world == 1:
+            return obj
+        box = [obj if self.rank == src else None]
+        dist.broadcast_object_list(box, src=src, group=self.group)
+        return box[0]
+
     def allgather_bytes(self, payload: bytes):
         if self.world == 1:
             return [payload]

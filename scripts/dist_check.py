@@ -55,6 +55,18 @@ ksvd_dict_learn(Xloc, K, init_dict=torch.from_numpy(Dh).to(dev), sparse_coder=en
 report["ksvd_errors_single"] = [h["error"] for h in h1]; report["ksvd_errors_sharded"] = [h["error"] for h in h2]
 ok2b = all(abs(a["error"] - b["error"]) <= 1e-3 * a["error"] for a, b in zip(h1, h2))
 
+# 2c. 'data' initialisation drawn over the global column space: same seed -> the sharded run starts from (and keeps) the
+# dictionary the single-GPU run on the whole set gets (dict_learning/utils.py:55-70 through init_dictionary_sharded)
+h3, h4 = [], []
+np.random.seed(77)
+Da1, _ = ksvd_dict_learn(Xfull, 256, init_dict="data", sparse_coder=enc, max_iter=2, approx=True, verbose=False, return_codes=True, history=h3)
+np.random.seed(77)
+Da2, _ = ksvd_dict_learn(Xloc, 256, init_dict="data", sparse_coder=enc, max_iter=2, approx=True, verbose=False, return_codes=True,
+                         history=h4, dist=ctx, exchange=ex)
+report["ksvd_data_init_max_dD"] = float((Da1 - Da2).abs().max())
+report["ksvd_data_init_errors"] = [[h["error"] for h in h3], [h["error"] for h in h4]]
+ok2c = report["ksvd_data_init_max_dD"] < 1e-4 and all(abs(a["error"] - b["error"]) <= 1e-3 * a["error"] for a, b in zip(h3, h4))
+
 # 3. ODL statistics
 n4, K4, b4 = 64, 512, 8192
 Xo = Xfull[:, :b4]; Do = torch.from_numpy(lo.synthetic_dictionary(K4, n4, seed=5)).to(dev)
@@ -69,7 +81,7 @@ dA = float((Aa - Ab).abs().max() / Aa.abs().max()); dDo = float((Da - Db).abs().
 report.update({"odl_rel_dA": dA, "odl_max_dD": dDo, "odl_bitwise_equal_to_1gpu": bool(torch.equal(Da, Db) and torch.equal(Aa, Ab) and torch.equal(Ba, Bb))})
 ok3 = dA < 1e-6 and dDo < 1e-6
 ex.close()
-okall = torch.tensor([int(ok1 and ok2 and ok2b and ok3)], device=dev); ctx.allreduce_sum_(okall)
+okall = torch.tensor([int(ok1 and ok2 and ok2b and ok2c and ok3)], device=dev); ctx.allreduce_sum_(okall)
 if ctx.rank == 0:
     report["all_ok"] = int(okall.item()) == ctx.world
     print(json.dumps(report))

@@ -124,8 +124,37 @@ def _gloo_worker(rank, world, port, N, out):
     ok_mb = (tuple(Xall.shape) == (n, world * b_loc) and torch.equal(Xall, want_X) and call.n_atoms == 7
              and torch.equal(call.idx[:, 0], torch.arange(world, dtype=torch.int32).repeat_interleave(b_loc))
              and torch.equal(call.val[:, 0], torch.arange(world, dtype=torch.float32).repeat_interleave(b_loc)))
+    # 'data' initialisation and unused-atom replacement over the GLOBAL column space (dict_learning/utils.py:55-70,
+    # ksvd.py:199-207): rank 0's RNG draws what a single process holding the concatenated shards draws, and every
+    # chosen column comes from its owner — the sharded dictionary equals the single-process one bit for bit
+    from lyssandra_b200.dict_learning import utils as dlu
+    rng2 = np.random.default_rng(7)
+    Xall_h = rng2.standard_normal((5, 41)).astype(np.float32)
+    Xall_h[:, [3, 17, 40]] = 0.0                                     # non-candidates (:55) on both shards
+    bounds = [0, 19, 41]                                             # uneven shards
+    Xloc = torch.from_numpy(np.ascontiguousarray(Xall_h[:, bounds[rank]:bounds[rank + 1]]))
+
+    def normalize_(M):                                               # stands in for the device norm_cols kernel
+        M /= (M.norm(dim=0, keepdim=True) + 1e-10)
+        return M
+    np.random.seed(123)
+    Dsh, unused_sh, offs = dlu.init_dictionary_sharded(ctx, Xloc, 6, normalize_=normalize_)
+    Dsh_before = Dsh.clone()
+    unused_sh = dlu.replace_unused_atoms_sharded(ctx, Xloc, Dsh, [4, 1], unused_sh, offs, normalize_=normalize_)
+    # the single-process run on the concatenated data, same seed, the reference's calls
+    np.random.seed(123)
+    cands = np.flatnonzero((Xall_h.astype(np.float64) ** 2).sum(axis=0) > 1e-6)
+    chosen = cands[np.random.choice(len(cands), size=6, replace=False)]
+    D1 = normalize_(torch.from_numpy(Xall_h[:, chosen].copy()))
+    un1 = np.array([c for c in cands if c not in set(chosen)])
+    ok_init = torch.equal(Dsh_before, D1) and list(offs) == bounds
+    for slot in [4, 1]:
+        pos = np.random.choice(len(un1), size=1)[0]
+        D1[:, slot:slot + 1] = normalize_(torch.from_numpy(Xall_h[:, [un1[pos]]].copy()))
+        un1 = np.delete(un1, pos)
+    ok_repl = torch.equal(Dsh, D1) and np.array_equal(unused_sh, un1)
     ok = (torch.allclose(A, Z @ Z.T) and torch.allclose(B, X @ Z.T) and int(cnt) == N
-          and gathered == [bytes([r]) * 4 for r in range(world)] and ok_mb)
+          and gathered == [bytes([r]) * 4 for r in range(world)] and ok_mb and ok_init and ok_repl)
     out[rank] = bool(ok)
     dist.destroy_process_group()
 
