@@ -323,3 +323,35 @@ def test_online_coder_and_gd_learner_shapes():
     oc = online_dictionary_coder(n_atoms=8, sparse_coder=_enc(2), batch_size=25, n_epochs=2)
     Z = oc(X)
     assert Z.shape == (8, 100) and oc.D.shape == (10, 8) and oc.A.shape == (8, 8) and oc.B.shape == (10, 8)
+
+
+def test_class_dict_learn_mirrors_the_reference_loop():
+    # class_dict_learn.py:98-139: one ksvd_dict_learn per class, blocks side by side; as written it returns after
+    # class 0 (`return D` inside the loop); all_classes=True trains every class
+    from lyssandra_b200.dict_learning import class_dict_learn, class_ksvd_coder
+    import lyssa.dict_learning.class_dict_learn as alias
+    assert alias.class_dict_learn is class_dict_learn
+    n, per, Kc = 16, 300, 8
+    X = np.concatenate([lo.synthetic_patches(per, n, seed=40 + c) for c in range(3)], axis=1).astype(np.float32)
+    y = np.repeat(np.arange(3), per)
+    perm = np.random.RandomState(0).permutation(3 * per)
+    X, y = np.ascontiguousarray(X[:, perm]), y[perm]
+    enc = _enc(2)
+    np.random.seed(11)
+    D_ref_style = class_dict_learn(X, y, n_class_atoms=[Kc] * 3, sparse_coders=[enc] * 3, max_iter=2, approx=True, verbose=False)
+    assert isinstance(D_ref_style, np.ndarray) and D_ref_style.shape == (n, 3 * Kc)
+    assert np.all(D_ref_style[:, Kc:] == 0) and np.allclose(np.linalg.norm(D_ref_style[:, :Kc], axis=0), 1.0, atol=1e-5)
+    np.random.seed(11)
+    D0, _ = ksvd_dict_learn(np.ascontiguousarray(X[:, y == 0]), Kc, init_dict="data", sparse_coder=enc, max_iter=2,
+                            approx=True, verbose=False)
+    assert np.array_equal(D_ref_style[:, :Kc], D0)
+    np.random.seed(11)
+    coder = class_ksvd_coder(n_class_atoms=Kc, sparse_coder=enc, max_iter=2, approx=True, verbose=False, all_classes=True)
+    D_all = coder(torch.from_numpy(X).to(DEV), y)
+    assert D_all.is_cuda and tuple(D_all.shape) == (n, 3 * Kc) and coder.n_class_atoms == [Kc] * 3
+    assert np.array_equal(D_all[:, :Kc].cpu().numpy(), D0)
+    assert torch.allclose(D_all.norm(dim=0), torch.ones(3 * Kc, device=DEV), atol=1e-5)
+    Z = coder.encode(torch.from_numpy(X).to(DEV))
+    assert tuple(Z.shape) == (3 * Kc, 3 * per)
+    with pytest.raises(NotImplementedError):
+        class_dict_learn(X, y, n_class_atoms=[Kc] * 3, sparse_coders=[enc] * 3, alpha=0.5, verbose=False)
