@@ -136,18 +136,48 @@ odl_accumulate_kernel(const float* __restrict__ X, int64_t xfs, int64_t xss,
         const int w0 = warp * per, w1 = min(words, w0 + per);
         float* dA = part + (size_t)warp * ldp;
         float* dB = dA + K;
+        constexpr int UB = 4;                                // users whose loads are in flight together
+        constexpr int FQ = LYS_MAX_FEATURES / 32;
         for (int w = w0; w < w1; ++w) {                      // this warp's users in ascending signal order
-            uint32_t bits = bitmap[w];                       // the same word in every lane: the loop is warp-uniform
+            uint32_t bits = bitmap[w];                       // the same word in every lane: the loops are warp-uniform
             while (bits) {
-                const int i = (w << 5) + __ffs(bits) - 1;
-                bits &= bits - 1;
-                const float za = val[(int64_t)i * k + slot[i]];
-                for (int j = lane; j < k; j += 32) {
-                    const int c = idx[(int64_t)i * k + j];
-                    if (c >= 0) dA[c] = fmaf(za, val[(int64_t)i * k + j], dA[c]);   // distinct atoms inside one code: no conflict
+                {   // k <= LYS_MAX_NONZERO = 32: one code per lane
+                    // the walk of a popular atom is a chain of dependent loads per user (slot -> coefficient -> code ->
+                    // signal): the loads of UB users are issued together, the additions keep the ascending order
+                    int ui[UB], uc[UB];
+                    float uz[UB], uv[UB], ux[UB][FQ];
+#pragma unroll
+                    for (int q = 0; q < UB; ++q) {
+                        ui[q] = bits ? (w << 5) + __ffs(bits) - 1 : -1;
+                        bits &= bits - 1;                    // 0 & anything stays 0
+                    }
+#pragma unroll
+                    for (int q = 0; q < UB; ++q) {
+                        uc[q] = -1; uz[q] = 0.f; uv[q] = 0.f;
+                        if (ui[q] >= 0) {
+                            const int64_t base = (int64_t)ui[q] * k;
+                            uz[q] = val[base + slot[ui[q]]];
+                            if (lane < k) { uc[q] = idx[base + lane]; uv[q] = val[base + lane]; }
+#pragma unroll
+                            for (int m = 0; m < FQ; ++m) {
+                                const int f = lane + 32 * m;
+                                ux[q][m] = (f < n) ? X[(int64_t)f * xfs + ui[q] * xss] : 0.f;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < UB; ++q) {
+                        if (ui[q] >= 0) {                    // warp-uniform
+                            if (uc[q] >= 0) dA[uc[q]] = fmaf(uz[q], uv[q], dA[uc[q]]);   // distinct atoms inside one code: no conflict
+#pragma unroll
+                            for (int m = 0; m < FQ; ++m) {
+                                const int f = lane + 32 * m;
+                                if (f < n) dB[f] = fmaf(ux[q][m], uz[q], dB[f]);
+                            }
+                            __syncwarp();
+                        }
+                    }
                 }
-                for (int f = lane; f < n; f += 32) dB[f] = fmaf(X[(int64_t)f * xfs + i * xss], za, dB[f]);
-                __syncwarp();
             }
         }
     }
