@@ -149,7 +149,9 @@ LYS_API int lys_corr_gemm(const float* X, int64_t x_feat_stride, int64_t x_sig_s
  * Z <- Z - eta * D^T (D Z - X) followed by keeping the k largest |Z| per signal; k <= 32.
  * Outputs and Z addressing as lys_bomp_encode; codes come out in descending order of the
  * selection key, ties to the lower atom index (the reference's argsort order on exact ties is
- * unspecified).  No Gram matrix is needed. */
+ * unspecified).  No Gram matrix is needed.  The values are fp32-faithful correlations: an fp32 GEMM on the two-kernel
+ * path, the three-product fp16 split accumulated in fp32 in tensor memory on the fused path (n <= 64, K in
+ * {256,...,1024}, k <= 10) — the error of an fp32 FMA dot product either way. */
 LYS_API size_t lys_thresh_workspace_bytes(int n, int K, int64_t N);
 LYS_API int lys_thresh_encode(const float* X, int64_t x_feat_stride, int64_t x_sig_stride,
                       const float* D, int64_t ldd, int n, int K, int64_t N, int k,
