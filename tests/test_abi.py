@@ -51,3 +51,23 @@ def test_pure_host_entry_points():
         _native.check(rc)
     out = ctypes.c_void_p()
     assert lib.lys_comm_create(0, 1, ctypes.byref(out)) == 0
+
+
+def test_build_fingerprint_travels_with_the_tree(tmp_path, monkeypatch):
+    """the library says what it was built from, and the hash does not depend on WHERE the tree lives: the GPU box runs
+    the repo from another directory, and a fingerprint over absolute paths made every rank of every launch rebuild the
+    .so there (and race on the half-written file)"""
+    import shutil
+    lib = _native.load()
+    here = _build._fingerprint()
+    assert lib.lys_build_fingerprint().decode() == here
+    assert _build.build() == _native.lib_path()                      # fresh: returns without compiling
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    moved = tmp_path / "elsewhere" / "lyssandra_b200"
+    shutil.copytree(os.path.join(root, "lyssandra_b200", "csrc"), moved / "csrc")
+    shutil.copytree(os.path.join(root, "include"), tmp_path / "elsewhere" / "include")
+    monkeypatch.setattr(_build, "CSRC", str(moved / "csrc"))
+    monkeypatch.setattr(_build, "_PKG", str(moved))
+    assert _build._fingerprint() == here
+    (moved / "csrc" / "common.cuh").write_text((moved / "csrc" / "common.cuh").read_text() + "\n// edited\n")
+    assert _build._fingerprint() != here
